@@ -1,0 +1,320 @@
+"""
+CPU ORACLE -- TEST INFRASTRUCTURE ONLY.  Nothing in the product package may import this file.
+
+This is a float64 CPU restatement of the kernel-ridge-regression hot path that the reference
+(NKI-CCB/sobolev_alignment) delegates to the third-party, un-vendored, un-pinned `falkon` package
+(import site: /root/reference/sobolev_alignment/krr_approx.py:29-34; call sites :182,227,232,262-268,
+284,314,403-404).  `falkon` is not installable in this image (no wheel, no source, no network), so the
+arithmetic below restates the *published* FALKON algorithm the reference cites
+(krr_approx.py:15-16: Meanti et al., NeurIPS 2020; Rudi, Carratino, Rosasco, NeurIPS 2017, Alg. 1):
+
+    T = chol(K_MM + eps*M*I)          (upper)           eps = 1e-5  (Falkon's float32 `pc_epsilon`)
+    A = chol(T T^T / M + lambda*I)    (upper)
+    rhs  = A^-T T^-T K_nM^T (Y / n)
+    BHB(u) = A^-T ( T^-T K_nM^T K_nM T^-1 A^-1 u / n + lambda * A^-1 u )
+    beta = CG(BHB, rhs, maxiter)      batched over the d columns, per-column step sizes,
+                                      residual recomputed from scratch every 10 iterations,
+                                      stop when max_c sqrt(r_c^T r_c) < 1e-7
+    alpha = T^-1 A^-1 beta ;  predict(X) = K(X, C) alpha
+
+PARITY STATUS: **parity unpinned** on the Falkon path -- the reference's own tests for this path hold
+no seeds, golden vectors or tolerances and are skipped whenever `falkon` is absent, which is the
+reference CI state (/root/reference/tests/test_krr_approx.py:96-106,207-233,251-265;
+/root/reference/.github/workflows/test.yaml:42-51).  The oracle is therefore pinned against the one
+piece of the reference that *does* run here: `KRRApprox(method="sklearn")` (krr_approx.py:176-178,251)
+-- with M = n, centres = all rows and sklearn's alpha = lambda*n the restated solver must reproduce the
+reference's predictions (see oracle/make_golden.py and tests/test_oracle.py).
+
+Kernel definitions (what `falkon.kernels.*` compute; restated from the Falkon documentation):
+    Gaussian   k = exp(-||a-b||^2 / (2 sigma^2))
+    Laplacian  k = exp(-||a-b||_2 / sigma)                 (L2 -- NOT sklearn's L1 "laplacian")
+    Matern     nu=0.5 -> Laplacian ; nu=inf -> Gaussian
+               nu=1.5: (1 + sqrt3 r) exp(-sqrt3 r)         r = ||a-b||_2 / sigma
+               nu=2.5: (1 + sqrt5 r + 5 r^2 / 3) exp(-sqrt5 r)
+
+Everything is computed in float64; distances are formed from explicit differences for small
+problems (no ||x||^2+||y||^2-2xy cancellation), so the oracle does not share the GPU path's
+rounding behaviour.
+"""
+
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+PC_EPSILON_F32 = 1e-5  # Falkon `pc_epsilon` for float32 inputs (the dtype the reference feeds)
+CG_EPSILON_F32 = 1e-7  # Falkon `cg_epsilon` for float32
+CG_TOLERANCE = 1e-7  # Falkon `cg_tolerance`
+CG_FULL_GRADIENT_EVERY = 10  # Falkon `cg_full_gradient_every`
+
+
+# ---------------------------------------------------------------------------------------------
+# kernels
+# ---------------------------------------------------------------------------------------------
+def canonical_kernel(kernel: str, nu=None):
+    """Map the reference's kernel names (krr_approx.py:59-71) to (family, nu)."""
+    k = kernel.lower()
+    if k in ("rbf", "gaussian"):
+        return "gaussian", None
+    if k == "laplacian":
+        return "laplacian", None
+    if k == "matern":
+        nu = 0.5 if nu is None else float(nu)
+        if nu == 0.5:
+            return "laplacian", None
+        if math.isinf(nu):
+            return "gaussian", None
+        if nu in (1.5, 2.5):
+            return "matern", nu
+        raise ValueError("nu must be one of 0.5, 1.5, 2.5, inf")
+    raise KeyError(kernel)
+
+
+def sq_dists(A: torch.Tensor, B: torch.Tensor, direct: bool | None = None) -> torch.Tensor:
+    """Pairwise squared euclidean distances in float64."""
+    A = A.to(torch.float64)
+    B = B.to(torch.float64)
+    if direct is None:
+        direct = A.shape[0] * B.shape[0] * A.shape[1] <= 2_000_000_000
+    if direct:
+        out = torch.empty(A.shape[0], B.shape[0], dtype=torch.float64)
+        step = max(1, int(32_000_000 // max(1, B.shape[0] * A.shape[1])))
+        for s in range(0, A.shape[0], step):
+            diff = A[s : s + step, None, :] - B[None, :, :]
+            out[s : s + step] = (diff * diff).sum(-1)
+        return out
+    na = (A * A).sum(1)[:, None]
+    nb = (B * B).sum(1)[None, :]
+    return (na + nb - 2.0 * (A @ B.T)).clamp_min_(0.0)
+
+
+def kernel_matrix(A, B, kernel: str, sigma: float, nu=None, direct=None) -> torch.Tensor:
+    """Dense k(A, B) in float64 (what `falkon.kernels.*Kernel.__call__` returns)."""
+    fam, nu = canonical_kernel(kernel, nu)
+    d2 = sq_dists(A, B, direct)
+    sigma = float(sigma)
+    if fam == "gaussian":
+        return torch.exp(-d2 / (2.0 * sigma * sigma))
+    r = torch.sqrt(d2.clamp_min(1e-20)) / sigma
+    if fam == "laplacian":
+        return torch.exp(-r)
+    if nu == 1.5:
+        s = math.sqrt(3.0) * r
+        return (1.0 + s) * torch.exp(-s)
+    s = math.sqrt(5.0) * r
+    return (1.0 + s + s * s / 3.0) * torch.exp(-s)
+
+
+def kmv(A, B, V, kernel, sigma, nu=None, direct=None) -> torch.Tensor:
+    """k(A, B) @ V -- the fused product the CUDA kernel computes."""
+    return kernel_matrix(A, B, kernel, sigma, nu, direct) @ V.to(torch.float64)
+
+
+# ---------------------------------------------------------------------------------------------
+# FALKON solver
+# ---------------------------------------------------------------------------------------------
+class Preconditioner:
+    """T and A factors of the Nystrom preconditioner."""
+
+    def __init__(self, K_MM: torch.Tensor, penalty: float, pc_eps: float = PC_EPSILON_F32):
+        M = K_MM.shape[0]
+        eye = torch.eye(M, dtype=torch.float64)
+        self.T = torch.linalg.cholesky(K_MM.to(torch.float64) + pc_eps * M * eye, upper=True)
+        self.A = torch.linalg.cholesky(self.T @ self.T.T / M + penalty * eye, upper=True)
+
+    def invT(self, v):
+        return torch.linalg.solve_triangular(self.T, v, upper=True)
+
+    def invTt(self, v):
+        return torch.linalg.solve_triangular(self.T.T, v, upper=False)
+
+    def invA(self, v):
+        return torch.linalg.solve_triangular(self.A, v, upper=True)
+
+    def invAt(self, v):
+        return torch.linalg.solve_triangular(self.A.T, v, upper=False)
+
+
+def conjugate_gradient(mmv, B, maxiter, cg_eps=CG_EPSILON_F32, tol=CG_TOLERANCE,
+                       full_every=CG_FULL_GRADIENT_EVERY, trace=None):
+    """Batched-column CG with per-column step sizes."""
+    X = torch.zeros_like(B)
+    R = B.clone()
+    P = R.clone()
+    rs_old = (R * R).sum(0)
+    n_iter = 0
+    for it in range(maxiter):
+        AP = mmv(P)
+        alpha = rs_old / ((P * AP).sum(0) + cg_eps)
+        X = X + P * alpha[None, :]
+        if (it + 1) % full_every == 0:
+            R = B - mmv(X)
+        else:
+            R = R - AP * alpha[None, :]
+        rs_new = (R * R).sum(0)
+        n_iter = it + 1
+        if trace is not None:
+            trace.append(float(rs_new.max().sqrt()))
+        if float(rs_new.max().sqrt()) < tol:
+            break
+        P = R + P * (rs_new / rs_old)[None, :]
+        rs_old = rs_new
+    return X, n_iter
+
+
+def falkon_fit(X, Y, centres, kernel, sigma, penalty, nu=None, maxiter=20, row_block=4096,
+               pc_eps=PC_EPSILON_F32, cg_eps=CG_EPSILON_F32, trace=None):
+    """
+    Restated `falkon.Falkon.fit`.  `centres` is the M x p centre matrix
+    (the caller picks the rows: Falkon draws them from an unseeded host RNG, so they are an INPUT
+    of every parity test).  Returns alpha [M x d] in float64.
+    """
+    X = X.to(torch.float64)
+    Y = Y.to(torch.float64)
+    C = centres.to(torch.float64)
+    n = X.shape[0]
+    prec = Preconditioner(kernel_matrix(C, C, kernel, sigma, nu), penalty, pc_eps)
+
+    def knm_t_knm(u, w=None):
+        """sum over row blocks of Kb^T (Kb u + w_b)   (Falkon `dmmv`)."""
+        out = torch.zeros(C.shape[0], Y.shape[1] if u is None else u.shape[1], dtype=torch.float64)
+        for s in range(0, n, row_block):
+            Kb = kernel_matrix(X[s : s + row_block], C, kernel, sigma, nu)
+            t = Kb @ u if u is not None else 0.0
+            if w is not None:
+                t = t + w[s : s + row_block]
+            out += Kb.T @ t
+        return out
+
+    rhs = prec.invAt(prec.invTt(knm_t_knm(None, Y / n)))
+
+    def bhb(u):
+        v = prec.invA(u)
+        cc = knm_t_knm(prec.invT(v))
+        return prec.invAt(prec.invTt(cc / n) + penalty * v)
+
+    beta, n_iter = conjugate_gradient(bhb, rhs, maxiter, cg_eps=cg_eps, trace=trace)
+    alpha = prec.invT(prec.invA(beta))
+    return alpha
+
+
+def falkon_predict(X, centres, alpha, kernel, sigma, nu=None, row_block=8192):
+    """Restated `falkon.Falkon.predict` = K(X, C) alpha  (krr_approx.py:314)."""
+    out = []
+    for s in range(0, X.shape[0], row_block):
+        out.append(kmv(X[s : s + row_block], centres, alpha, kernel, sigma, nu))
+    return torch.cat(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# alignment block (sobolev_alignment.py:929-988, kernel_operations.py:12-16)
+# ---------------------------------------------------------------------------------------------
+def mat_inv_sqrt(M, threshold=1e-6):
+    """kernel_operations.py:12-16 restated (SVD inverse square root, small singular values zeroed)."""
+    M = np.asarray(M, dtype=np.float64)
+    u, s, v = np.linalg.svd(M)
+    s = np.array([1.0 / np.sqrt(x) if x > threshold else 0.0 for x in s])
+    return v.T.dot(np.diag(s)).dot(u.T)
+
+
+def alignment(alpha_s, C_s, alpha_t, C_t, kernel, sigma, nu=None):
+    """
+    sobolev_alignment.py:929-988 restated: M_X, M_Y, M_XY, cosine similarity matrix, principal
+    angles (singular values of the cosine similarity matrix) and principal-vector coefficients.
+    """
+    a_s = alpha_s.to(torch.float64)
+    a_t = alpha_t.to(torch.float64)
+    M_X = (a_s.T @ kernel_matrix(C_s, C_s, kernel, sigma, nu) @ a_s).numpy()
+    M_Y = (a_t.T @ kernel_matrix(C_t, C_t, kernel, sigma, nu) @ a_t).numpy()
+    M_XY = (a_s.T @ kernel_matrix(C_s, C_t, kernel, sigma, nu) @ a_t).numpy()
+    sx, sy = mat_inv_sqrt(M_X), mat_inv_sqrt(M_Y)
+    cosine_sim = sx.dot(M_XY).dot(sy)
+    u, s, vt = np.linalg.svd(cosine_sim, full_matrices=False)
+    pv_s = u.T.dot(sx).dot(a_s.T.numpy())
+    pv_t = vt.dot(sy).dot(a_t.T.numpy())
+    return {
+        "M_X": M_X, "M_Y": M_Y, "M_XY": M_XY, "cosine_sim": cosine_sim,
+        "principal_angles": s, "pv_source": pv_s, "pv_target": pv_t,
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# float32 CPU port used as the timed `cpu_baseline` ("Baseline A"):
+# same algorithm, Falkon's CPU structure (row-blocked addmm for -2 Xb C^T + pointwise ops).
+# ---------------------------------------------------------------------------------------------
+def kernel_block_f32(Xb, nXb, C, nC, kernel, sigma, nu=None):
+    fam, nu = canonical_kernel(kernel, nu)
+    d2 = torch.addmm(nXb[:, None] + nC[None, :], Xb, C.T, alpha=-2.0).clamp_min_(1e-20)
+    if fam == "gaussian":
+        return d2.mul_(-1.0 / (2.0 * sigma * sigma)).exp_()
+    r = d2.sqrt_().mul_(1.0 / sigma)
+    if fam == "laplacian":
+        return r.neg_().exp_()
+    if nu == 1.5:
+        s = r.mul_(math.sqrt(3.0))
+        return (1.0 + s) * torch.exp(-s)
+    s = r.mul_(math.sqrt(5.0))
+    return (1.0 + s + s * s / 3.0) * torch.exp(-s)
+
+
+def dmmv_pass_f32(X, C, u, w, kernel, sigma, nu=None, row_block=4096):
+    """One streamed K_nM^T (K_nM u + w) pass in float32 -- the unit the CPU baseline times."""
+    X = X.float()
+    C = C.float()
+    nC = (C * C).sum(1)
+    out = torch.zeros(C.shape[0], (u if u is not None else w).shape[1], dtype=torch.float32)
+    for s in range(0, X.shape[0], row_block):
+        Xb = X[s : s + row_block]
+        Kb = kernel_block_f32(Xb, (Xb * Xb).sum(1), C, nC, kernel, sigma, nu)
+        t = Kb @ u if u is not None else 0.0
+        if w is not None:
+            t = t + w[s : s + row_block]
+        out += Kb.T @ t
+    return out
+
+
+def kmv_f32(X, C, V, kernel, sigma, nu=None, row_block=4096):
+    """K(X, C) @ V in float32 with the GEMM-based distance -- one `kmv`, CPU baseline unit."""
+    X = X.float()
+    C = C.float()
+    nC = (C * C).sum(1)
+    out = torch.empty(X.shape[0], V.shape[1], dtype=torch.float32)
+    for s in range(0, X.shape[0], row_block):
+        Xb = X[s : s + row_block]
+        Kb = kernel_block_f32(Xb, (Xb * Xb).sum(1), C, nC, kernel, sigma, nu)
+        out[s : s + row_block] = Kb @ V
+    return out
+
+
+def falkon_fit_f32(X, Y, centres, kernel, sigma, penalty, nu=None, maxiter=20, row_block=4096):
+    """Whole float32 CPU fit (Baseline A); same steps as `falkon_fit`."""
+    X = X.float()
+    Y = Y.float()
+    C = centres.float()
+    n, M = X.shape[0], C.shape[0]
+    nC = (C * C).sum(1)
+    K = kernel_block_f32(C, nC, C, nC, kernel, sigma, nu)
+    K.diagonal().add_(PC_EPSILON_F32 * M)
+    T = torch.linalg.cholesky(K, upper=True)
+    A = T @ T.T
+    A.div_(M)
+    A.diagonal().add_(penalty)
+    A = torch.linalg.cholesky(A, upper=True)
+    st = torch.linalg.solve_triangular
+
+    def invT(v): return st(T, v, upper=True)
+    def invTt(v): return st(T.T, v, upper=False)
+    def invA(v): return st(A, v, upper=True)
+    def invAt(v): return st(A.T, v, upper=False)
+
+    rhs = invAt(invTt(dmmv_pass_f32(X, C, None, Y / n, kernel, sigma, nu, row_block)))
+
+    def bhb(u):
+        v = invA(u)
+        cc = dmmv_pass_f32(X, C, invT(v), None, kernel, sigma, nu, row_block)
+        return invAt(invTt(cc / n) + penalty * v)
+
+    beta, _ = conjugate_gradient(bhb, rhs, maxiter)
+    return invT(invA(beta))
