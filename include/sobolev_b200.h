@@ -1,0 +1,125 @@
+/*
+ * sobolev_b200 -- C ABI of the B200-native kernel-ridge-regression hot path.
+ *
+ * This is the boundary a maintainer of NKI-CCB/sobolev_alignment binds in place of the third-party
+ * `falkon` package that `sobolev_alignment/krr_approx.py:29-34` imports.  The reference is Python, so
+ * the binding is a `ctypes.CDLL` (see INTEGRATION.md and sobolev_alignment_b200/_native.py); every
+ * entry point below names the reference interface (file:line in /root/reference) it replaces.
+ * `[ext]` marks an interface that lives in the external `falkon` dependency and is reached through the
+ * cited reference call site.
+ *
+ * Conventions
+ *   - return value 0 = success, anything else = failure; `sa_last_error()` then returns a
+ *     thread-local human readable message.  No C++ exception crosses this boundary.
+ *   - every pointer is a DEVICE pointer unless the name says host; the caller owns all memory
+ *     (the library never allocates device memory and never synchronises the device).
+ *   - `stream` is a `cudaStream_t` passed as `void*`; all work is enqueued on it.
+ *   - matrices are row-major; `ld*` is the row stride in ELEMENTS.
+ *   - "prepared" operands are what `sa_prep` writes: fp16 rows, centred and scaled so that the
+ *     euclidean distance between prepared rows is the kernel argument, row stride a multiple of 64,
+ *     zero padded; plus fp32 squared norms of the ROUNDED rows in an array whose length is padded
+ *     to a multiple of 256 (padding = 0).
+ *   - `dp` is the padded number of right-hand-side columns: multiple of 4, 4 <= dp <= 32.
+ */
+#ifndef SOBOLEV_B200_H_
+#define SOBOLEV_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* kernel families: falkon.kernels.{GaussianKernel,LaplacianKernel,MaternKernel} [ext],
+ * constructed at krr_approx.py:67-70,182 */
+enum {
+  SA_KERNEL_GAUSSIAN = 0, /* exp(-kscale * D^2)                      kscale = 1 / (2 sigma^2)      */
+  SA_KERNEL_LAPLACIAN = 1, /* exp(-r),                  r = kscale*D  kscale = 1 / sigma            */
+  SA_KERNEL_MATERN15 = 2,  /* (1 + sqrt3 r) exp(-sqrt3 r)                                           */
+  SA_KERNEL_MATERN25 = 3   /* (1 + sqrt5 r + 5 r^2/3) exp(-sqrt5 r)                                 */
+};
+
+int sa_version(void);
+const char* sa_last_error(void);
+
+/* Number of SMs / bytes of dynamic shared memory the fused kernel was configured with for the
+ * current device (diagnostics for bench.py). */
+int sa_device_info(int* sm_count, int* smem_bytes);
+
+/*
+ * Row preparation (falkon `square_norm` + the implicit fp32 operands of `fmmv` [ext]; the input is
+ * what `KRRApprox.fit` hands over at krr_approx.py:227 / `transform` at :314):
+ *   out[i, j] = fp16( (X[i, j] - shift[j]) * scale[j] * gscale ),  j < p ;  0 for p <= j < ldo
+ *   norms[i]  = sum_j float(out[i, j])^2 ;  norms[i] = 0 for n <= i < norms_len
+ * `shift` / `scale` may be NULL (0 / 1).  X is never written.
+ */
+int sa_prep(void* stream, const float* X, int64_t n, int64_t p, int64_t ldx, const float* shift,
+            const float* scale, float gscale, void* out_f16, int64_t ldo, float* norms,
+            int64_t norms_len);
+
+/*
+ * Fused kernel-matrix x matrix product, K never materialised (falkon `Kernel.mmv` and each half of
+ * `Kernel.dmmv` [ext]; reached from `Falkon.fit` krr_approx.py:227 and `Falkon.predict` :314):
+ *   out[a x dp] += k(A, B) @ V[b x dp]
+ * A [a x p_pad], B [b x p_pad] are prepared operands with norms nA, nB.  `out` is accumulated into
+ * with atomic adds (the caller zeroes it for a plain product).  `symmetric` != 0 asserts A == B
+ * so the exact zero distance is used on the diagonal.
+ */
+int sa_kmv(void* stream, int kernel, float kscale, const void* A, const float* nA, int64_t a,
+           int64_t lda, const void* B, const float* nB, int64_t b, int64_t ldb, int64_t p_pad,
+           const float* V, int dp, float* out, int symmetric);
+
+/*
+ * Dense kernel matrix (falkon `Kernel.__call__` [ext]; called as `kernel_(A, B)` at
+ * sobolev_alignment.py:950,955-958 and tests/test_krr_approx.py:255, and for K_MM inside
+ * `Falkon.fit`):  out[a x b] = k(A, B), fp32, row stride ldo.
+ */
+int sa_kdense(void* stream, int kernel, float kscale, const void* A, const float* nA, int64_t a,
+              int64_t lda, const void* B, const float* nB, int64_t b, int64_t ldb, int64_t p_pad,
+              float* out, int64_t ldo, int symmetric);
+
+/*
+ * Nystrom preconditioner (falkon `FalkonPreconditioner.init`: potrf / lauum / mul_triang [ext],
+ * reached from krr_approx.py:227).  All matrices fp32 row-major, LOWER triangle significant;
+ * T = L^T and A = LA^T are the upper factors of the published algorithm.
+ *
+ * sa_potrf: in-place blocked Cholesky A = L L^T (lower).  `invdiag` receives the inverses of the
+ * 128x128 diagonal blocks of L ( ceil(M/128) blocks of 128*128 floats ); they are what the
+ * triangular solves use.  `info` (device int) is set to 1 + index of the first non-positive pivot,
+ * or left 0.
+ */
+int sa_potrf(void* stream, float* A, int64_t M, int64_t lda, float* invdiag, int* info);
+
+/* G(lower) = alpha * L^T L + beta * I   (falkon `lauum` + `mul_triang` + add-diagonal [ext]) */
+int sa_ltl(void* stream, const float* L, int64_t M, int64_t ldl, float* G, int64_t ldg, float alpha,
+           float beta);
+
+/* A[i, i] += value */
+int sa_add_diag(void* stream, float* A, int64_t M, int64_t lda, float value);
+
+/*
+ * Triangular solves with a Cholesky factor from sa_potrf (cuBLAS `trsm` inside falkon's
+ * `invT / invTt / invA / invAt` [ext]):  B[M x dp] <- L^-1 B (transpose = 0) or L^-T B (transpose = 1).
+ */
+int sa_trsm(void* stream, const float* L, int64_t M, int64_t ldl, const float* invdiag, float* B,
+            int dp, int transpose);
+
+/*
+ * Conjugate-gradient vector kernels (falkon `ConjugateGradient.solve` [ext]); all M x dp fp32.
+ * sa_coldot:   out[c] = sum_i P[i, c] * Q[i, c]                    (out is overwritten)
+ * sa_cg_update: alpha_c = rs_old[c] / (pAp[c] + eps);  X += P alpha;  R -= AP alpha (if AP != NULL);
+ *              rs_new[c] = sum_i R[i, c]^2 (if R updated)
+ * sa_cg_direction: P = R + (rs_new / rs_old) P
+ * sa_axpby:    Y = a * X + b * Y   (elementwise, len floats)
+ */
+int sa_coldot(void* stream, const float* P, const float* Q, int64_t M, int dp, float* out);
+int sa_cg_update(void* stream, int64_t M, int dp, const float* P, const float* AP, float* X,
+                 float* R, const float* rs_old, const float* pAp, float eps, float* rs_new);
+int sa_cg_direction(void* stream, int64_t M, int dp, const float* R, float* P, const float* rs_new,
+                    const float* rs_old);
+int sa_axpby(void* stream, int64_t len, float a, const float* X, float b, float* Y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOBOLEV_B200_H_ */

@@ -1,0 +1,241 @@
+"""
+ctypes binding of libsobolev_b200.so (the C ABI in include/sobolev_b200.h).
+
+This is the only compute backend of the package: if the shared library is missing, or a call is
+made without a CUDA device, it raises -- there is no CPU or eager-PyTorch fallback.  PyTorch is
+used for device memory and streams only; every pointer handed to the library is `tensor.data_ptr()`
+and every launch goes to `torch.cuda.current_stream()`.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+import torch
+
+_LIB_NAME = "libsobolev_b200.so"
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", _LIB_NAME)
+
+KERNEL_IDS = {"gaussian": 0, "laplacian": 1, "matern15": 2, "matern25": 3}
+TILE = 128  # order granularity of the dense fp32 routines
+NORM_PAD = 256  # norm arrays are padded to a multiple of this
+FEAT_PAD = 64  # prepared rows are padded to a multiple of this
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_SIGNATURES = {
+    "sa_version": (c_int, []),
+    "sa_last_error": (c_char_p, []),
+    "sa_device_info": (c_int, [c_void_p, c_void_p]),
+    "sa_prep": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_float,
+                        c_void_p, c_int64, c_void_p, c_int64]),
+    "sa_kmv": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                       c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int]),
+    "sa_kdense": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
+                          c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int]),
+    "sa_potrf": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "sa_ltl": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_float]),
+    "sa_add_diag": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float]),
+    "sa_trsm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int]),
+    "sa_coldot": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "sa_cg_update": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_float, c_void_p]),
+    "sa_cg_direction": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sa_axpby": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_float, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (no CUDA call is made here)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise NativeLibraryError(
+                f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `sobolev_alignment_b200/csrc/build.sh` (nvcc, sm_100a). There is no fallback path.")
+        lib = ctypes.CDLL(_LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        msg = load().sa_last_error()
+        raise NativeLibraryError(f"libsobolev_b200 call failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise NativeLibraryError(f"{name} must be a CUDA tensor (the native path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------------------
+class Prepared:
+    """fp16 rows (centred, scaled, zero padded to a multiple of 64 features) + fp32 squared norms."""
+
+    __slots__ = ("data", "norms", "n", "p", "p_pad")
+
+    def __init__(self, data, norms, n, p):
+        self.data, self.norms, self.n, self.p, self.p_pad = data, norms, n, p, data.shape[1]
+
+
+def prep(X: torch.Tensor, shift: torch.Tensor | None, scale: torch.Tensor | None, gscale: float,
+         out: Prepared | None = None, row_offset: int = 0) -> Prepared:
+    """sa_prep on a [n x p] fp32 CUDA tensor (row stride may exceed p)."""
+    lib = load()
+    if not X.is_cuda or X.dtype != torch.float32 or X.dim() != 2 or X.stride(1) != 1:
+        raise NativeLibraryError("prep expects a 2-D float32 CUDA tensor with unit column stride")
+    n, p = X.shape
+    if out is None:
+        p_pad = round_up(p, FEAT_PAD)
+        data = torch.empty(n, p_pad, dtype=torch.float16, device=X.device)
+        norms = torch.empty(round_up(max(n, 1), NORM_PAD), dtype=torch.float32, device=X.device)
+        out = Prepared(data, norms, n, p)
+        norms_len = norms.numel()
+        dptr, nptr = data.data_ptr(), norms.data_ptr()
+    else:
+        # fill rows [row_offset, row_offset + n) of an existing buffer (chunked staging)
+        if row_offset % NORM_PAD and row_offset + n != out.n:
+            pass
+        dptr = out.data.data_ptr() + row_offset * out.p_pad * 2
+        nptr = out.norms.data_ptr() + row_offset * 4
+        last = row_offset + n == out.n
+        norms_len = (out.norms.numel() - row_offset) if last else n
+    if n == 0:
+        return out
+    _check(lib.sa_prep(_stream(), X.data_ptr(), n, p, X.stride(0), _ptr(shift), _ptr(scale),
+                       float(gscale), dptr, out.p_pad, nptr, norms_len))
+    return out
+
+
+def alloc_prepared(n: int, p: int, device) -> Prepared:
+    p_pad = round_up(p, FEAT_PAD)
+    data = torch.empty(n, p_pad, dtype=torch.float16, device=device)
+    norms = torch.zeros(round_up(max(n, 1), NORM_PAD), dtype=torch.float32, device=device)
+    return Prepared(data, norms, n, p)
+
+
+def kmv(kernel_id: int, kscale: float, A: Prepared, B: Prepared, V: torch.Tensor, out: torch.Tensor,
+        symmetric: bool = False, a_rows: slice | None = None):
+    """out[a x dp] += k(A, B) @ V[b x dp]   (out must be zeroed by the caller for a plain product)."""
+    lib = load()
+    _req(V, torch.float32, "V")
+    _req(out, torch.float32, "out")
+    dp = V.shape[1]
+    if V.shape[0] != B.n or out.shape != (A.n, dp):
+        raise ValueError(f"shape mismatch: V {tuple(V.shape)}, out {tuple(out.shape)}, a={A.n}, b={B.n}")
+    if A.p_pad != B.p_pad:
+        raise ValueError("A and B were prepared with different feature counts")
+    _check(lib.sa_kmv(_stream(), kernel_id, float(kscale), A.data.data_ptr(), A.norms.data_ptr(), A.n,
+                      A.p_pad, B.data.data_ptr(), B.norms.data_ptr(), B.n, B.p_pad, A.p_pad,
+                      V.data_ptr(), dp, out.data_ptr(), int(symmetric)))
+    return out
+
+
+def kdense(kernel_id: int, kscale: float, A: Prepared, B: Prepared, out: torch.Tensor,
+           symmetric: bool = False):
+    """out[:a, :b] = k(A, B); `out` is a 2-D fp32 CUDA tensor whose row stride may exceed b."""
+    lib = load()
+    if not out.is_cuda or out.dtype != torch.float32 or out.stride(1) != 1:
+        raise NativeLibraryError("kdense output must be a float32 CUDA tensor with unit column stride")
+    if out.shape[0] < A.n or out.shape[1] < B.n:
+        raise ValueError("output too small")
+    _check(lib.sa_kdense(_stream(), kernel_id, float(kscale), A.data.data_ptr(), A.norms.data_ptr(), A.n,
+                         A.p_pad, B.data.data_ptr(), B.norms.data_ptr(), B.n, B.p_pad, A.p_pad,
+                         out.data_ptr(), out.stride(0), int(symmetric)))
+    return out
+
+
+def potrf(A: torch.Tensor, invdiag: torch.Tensor, info: torch.Tensor):
+    _req(A, torch.float32, "A")
+    _req(invdiag, torch.float32, "invdiag")
+    _check(load().sa_potrf(_stream(), A.data_ptr(), A.shape[0], A.stride(0), invdiag.data_ptr(),
+                           info.data_ptr()))
+
+
+def ltl(L: torch.Tensor, G: torch.Tensor, alpha: float, beta: float):
+    _req(L, torch.float32, "L")
+    _req(G, torch.float32, "G")
+    _check(load().sa_ltl(_stream(), L.data_ptr(), L.shape[0], L.stride(0), G.data_ptr(), G.stride(0),
+                         float(alpha), float(beta)))
+
+
+def add_diag(A: torch.Tensor, m: int, value: float):
+    _req(A, torch.float32, "A")
+    _check(load().sa_add_diag(_stream(), A.data_ptr(), m, A.stride(0), float(value)))
+
+
+def trsm(L: torch.Tensor, invdiag: torch.Tensor, B: torch.Tensor, transpose: bool):
+    _req(L, torch.float32, "L")
+    _req(B, torch.float32, "B")
+    if B.shape[0] != L.shape[0]:
+        raise ValueError("rhs rows must equal the (padded) matrix order")
+    _check(load().sa_trsm(_stream(), L.data_ptr(), L.shape[0], L.stride(0), invdiag.data_ptr(),
+                          B.data_ptr(), B.shape[1], int(transpose)))
+    return B
+
+
+def coldot(P: torch.Tensor, Q: torch.Tensor, out: torch.Tensor):
+    _req(P, torch.float32, "P")
+    _req(Q, torch.float32, "Q")
+    _check(load().sa_coldot(_stream(), P.data_ptr(), Q.data_ptr(), P.shape[0], P.shape[1], out.data_ptr()))
+    return out
+
+
+def cg_update(P, AP, X, R, rs_old, pAp, eps: float, rs_new):
+    _req(P, torch.float32, "P")
+    _check(load().sa_cg_update(_stream(), P.shape[0], P.shape[1], P.data_ptr(), _ptr(AP), X.data_ptr(),
+                               _ptr(R), rs_old.data_ptr(), pAp.data_ptr(), float(eps), _ptr(rs_new)))
+
+
+def cg_direction(R, P, rs_new, rs_old):
+    _check(load().sa_cg_direction(_stream(), P.shape[0], P.shape[1], R.data_ptr(), P.data_ptr(),
+                                  rs_new.data_ptr(), rs_old.data_ptr()))
+
+
+def axpby(a: float, X: torch.Tensor, b: float, Y: torch.Tensor):
+    _req(X, torch.float32, "X")
+    _req(Y, torch.float32, "Y")
+    if X.numel() != Y.numel():
+        raise ValueError("size mismatch")
+    _check(load().sa_axpby(_stream(), X.numel(), float(a), X.data_ptr(), float(b), Y.data_ptr()))
+    return Y
+
+
+def device_info():
+    sms, smem = c_int(0), c_int(0)
+    _check(load().sa_device_info(ctypes.byref(sms), ctypes.byref(smem)))
+    return sms.value, smem.value

@@ -1,0 +1,559 @@
+// fp32 dense linear algebra of the Nystrom preconditioner and the CG vector updates.
+//
+// Everything here works on matrices whose order is a multiple of 128 (the host pads K_MM with an
+// identity block, which leaves the Cholesky factors and every solve unchanged), row-major, lower
+// triangle significant:
+//   sa_potrf   blocked right-looking Cholesky: 128x128 diagonal factor+inverse in shared memory,
+//              panel = A * inv(L_kk)^T, trailing update = register-tiled SIMT SGEMM (NT)
+//   sa_ltl     G = alpha L^T L + beta I on the lower tiles (TN SGEMM over the rows below the tile)
+//   sa_trsm    block forward / backward substitution; one launch per 128-row block step, each CTA
+//              streams one 128x128 tile of L (coalesced 128-bit loads) against the M x dp rhs
+//   sa_coldot / sa_cg_update / sa_cg_direction / sa_axpby   CG vector kernels, coalesced over the
+//              row-major M x dp layout with warp-shuffle + shared-memory column reductions
+//
+// Replaces falkon `FalkonPreconditioner` (potrf, lauum, mul_triang, trsm) and
+// `ConjugateGradient.solve` [external dependency], reached from
+// /root/reference/sobolev_alignment/krr_approx.py:227.
+#include "../../include/sobolev_b200.h"
+#include "common.cuh"
+
+namespace sab {
+namespace la {
+
+constexpr int TS = 128;        // tile size
+constexpr int KC = 16;         // k chunk of the SGEMM
+constexpr int LDT = TS + 4;    // padded shared-memory row of the SGEMM operand tiles
+
+enum { MODE_PANEL = 0, MODE_SYRK = 1, MODE_LTL = 2 };
+
+// --------------------------------------------------------------------------------------------
+// 128x128 SIMT SGEMM tile: 256 threads, each 8x8 outputs split as 2x2 groups of 4x4 so that every
+// shared-memory read is a conflict-free 128-bit load.
+// --------------------------------------------------------------------------------------------
+struct GemmSmem {
+  float a[2][KC][LDT];
+  float b[2][KC][LDT];
+};
+
+// operand stored [row][k] in global (k contiguous): transpose while staging
+__device__ __forceinline__ void load_nt(const float* __restrict__ src, long long ld, int kc0,
+                                        float4 (&reg)[2]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int idx = threadIdx.x + i * 256;
+    const int r = idx >> 2, kq = idx & 3;
+    reg[i] = *reinterpret_cast<const float4*>(src + static_cast<long long>(r) * ld + kc0 + kq * 4);
+  }
+}
+__device__ __forceinline__ void store_nt(float (*dst)[LDT], const float4 (&reg)[2]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int idx = threadIdx.x + i * 256;
+    const int r = idx >> 2, kq = idx & 3;
+    dst[kq * 4 + 0][r] = reg[i].x;
+    dst[kq * 4 + 1][r] = reg[i].y;
+    dst[kq * 4 + 2][r] = reg[i].z;
+    dst[kq * 4 + 3][r] = reg[i].w;
+  }
+}
+// operand stored [k][col] in global (col contiguous): straight copy
+__device__ __forceinline__ void load_tn(const float* __restrict__ src, long long ld, int kc0,
+                                        float4 (&reg)[2]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int idx = threadIdx.x + i * 256;
+    const int kk = idx >> 5, cq = idx & 31;
+    reg[i] = *reinterpret_cast<const float4*>(src + static_cast<long long>(kc0 + kk) * ld + cq * 4);
+  }
+}
+__device__ __forceinline__ void store_tn(float (*dst)[LDT], const float4 (&reg)[2]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int idx = threadIdx.x + i * 256;
+    const int kk = idx >> 5, cq = idx & 31;
+    *reinterpret_cast<float4*>(&dst[kk][cq * 4]) = reg[i];
+  }
+}
+
+template <bool TN>
+__device__ __forceinline__ void gemm_tile(const float* __restrict__ A, const float* __restrict__ B,
+                                          long long lda, long long ldb, int ksteps, GemmSmem& sm,
+                                          float (&acc)[8][8]) {
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float4 ra[2], rb[2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  if (TN) { load_tn(A, lda, 0, ra); load_tn(B, ldb, 0, rb); store_tn(sm.a[0], ra); store_tn(sm.b[0], rb); }
+  else    { load_nt(A, lda, 0, ra); load_nt(B, ldb, 0, rb); store_nt(sm.a[0], ra); store_nt(sm.b[0], rb); }
+  __syncthreads();
+  int cur = 0;
+  for (int kt = 0; kt < ksteps; ++kt) {
+    const bool more = kt + 1 < ksteps;
+    if (more) {
+      if (TN) { load_tn(A, lda, (kt + 1) * KC, ra); load_tn(B, ldb, (kt + 1) * KC, rb); }
+      else    { load_nt(A, lda, (kt + 1) * KC, ra); load_nt(B, ldb, (kt + 1) * KC, rb); }
+    }
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sm.a[cur][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sm.a[cur][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&sm.b[cur][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&sm.b[cur][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) {
+      if (TN) { store_tn(sm.a[cur ^ 1], ra); store_tn(sm.b[cur ^ 1], rb); }
+      else    { store_nt(sm.a[cur ^ 1], ra); store_nt(sm.b[cur ^ 1], rb); }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+}
+
+// rows/cols owned by this thread inside the 128x128 tile
+__device__ __forceinline__ int tile_row(int i) { return (i < 4 ? 0 : 64) + (threadIdx.x >> 4) * 4 + (i & 3); }
+__device__ __forceinline__ int tile_col(int j) { return (j < 4 ? 0 : 64) + (threadIdx.x & 15) * 4; }
+
+__device__ __forceinline__ void tri_index(int t, int& i, int& j) {
+  // t = i (i + 1) / 2 + j, 0 <= j <= i
+  i = static_cast<int>((sqrtf(8.f * static_cast<float>(t) + 1.f) - 1.f) * 0.5f);
+  while ((i + 1) * (i + 2) / 2 <= t) ++i;
+  while (i * (i + 1) / 2 > t) --i;
+  j = t - i * (i + 1) / 2;
+}
+
+// PANEL : A[k0+128+bi*128 .., k0..k0+128) <- A_panel * invL^T          (in place)
+// SYRK  : C(i, j) -= L(i, k) L(j, k)^T for block indices i >= j > k
+// LTL   : G(i, j)  = alpha * sum_{l >= i} L(l, i)^T L(l, j) + beta * I
+template <int MODE>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(float* __restrict__ A, long long lda, const float* __restrict__ aux, long long ldaux,
+             int k, int nblk, float alpha, float beta) {
+  __shared__ GemmSmem sm;
+  float acc[8][8];
+  if (MODE == MODE_PANEL) {
+    const long long r0 = static_cast<long long>(k + 1 + blockIdx.x) * TS;
+    float* panel = A + r0 * lda + static_cast<long long>(k) * TS;
+    gemm_tile<false>(panel, aux, lda, TS, TS / KC, sm, acc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float* dst = panel + static_cast<long long>(tile_row(i)) * lda;
+#pragma unroll
+      for (int jh = 0; jh < 2; ++jh)
+        *reinterpret_cast<float4*>(dst + tile_col(jh * 4)) =
+            make_float4(acc[i][jh * 4], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
+    }
+  } else if (MODE == MODE_SYRK) {
+    int ti, tj;
+    tri_index(blockIdx.x, ti, tj);
+    const long long bi = k + 1 + ti, bj = k + 1 + tj;
+    const float* Li = A + bi * TS * lda + static_cast<long long>(k) * TS;
+    const float* Lj = A + bj * TS * lda + static_cast<long long>(k) * TS;
+    gemm_tile<false>(Li, Lj, lda, lda, TS / KC, sm, acc);
+    float* C = A + bi * TS * lda + bj * TS;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float* dst = C + static_cast<long long>(tile_row(i)) * lda;
+#pragma unroll
+      for (int jh = 0; jh < 2; ++jh) {
+        float4* p = reinterpret_cast<float4*>(dst + tile_col(jh * 4));
+        float4 c = *p;
+        c.x -= acc[i][jh * 4];
+        c.y -= acc[i][jh * 4 + 1];
+        c.z -= acc[i][jh * 4 + 2];
+        c.w -= acc[i][jh * 4 + 3];
+        *p = c;
+      }
+    }
+  } else {
+    int ti, tj;
+    tri_index(blockIdx.x, ti, tj);
+    const float* L = aux;
+    const float* Li = L + static_cast<long long>(ti) * TS * ldaux + static_cast<long long>(ti) * TS;
+    const float* Lj = L + static_cast<long long>(ti) * TS * ldaux + static_cast<long long>(tj) * TS;
+    gemm_tile<true>(Li, Lj, ldaux, ldaux, (nblk - ti) * (TS / KC), sm, acc);
+    float* G = A + static_cast<long long>(ti) * TS * lda + static_cast<long long>(tj) * TS;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = tile_row(i);
+      float* dst = G + static_cast<long long>(r) * lda;
+#pragma unroll
+      for (int jh = 0; jh < 2; ++jh) {
+        const int c = tile_col(jh * 4);
+        float4 v = make_float4(alpha * acc[i][jh * 4], alpha * acc[i][jh * 4 + 1],
+                               alpha * acc[i][jh * 4 + 2], alpha * acc[i][jh * 4 + 3]);
+        if (ti == tj) {
+          if (c + 0 == r) v.x += beta;
+          if (c + 1 == r) v.y += beta;
+          if (c + 2 == r) v.z += beta;
+          if (c + 3 == r) v.w += beta;
+        }
+        *reinterpret_cast<float4*>(dst + c) = v;
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// 128x128 diagonal block: Cholesky in shared memory, then the explicit inverse of the factor.
+// --------------------------------------------------------------------------------------------
+constexpr int LDD = TS + 1;
+
+__global__ void __launch_bounds__(256)
+diag_factor_kernel(float* __restrict__ A, long long lda, int k, float* __restrict__ invdiag,
+                   int* __restrict__ info) {
+  extern __shared__ float dsm[];
+  float* Ls = dsm;                 // [128][129]
+  float* Xs = dsm + TS * LDD;      // [128][129]
+  float* blk = A + static_cast<long long>(k) * TS * lda + static_cast<long long>(k) * TS;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < TS * TS / 4; idx += 256) {
+    const int r = idx >> 5, cq = idx & 31;
+    const float4 v = *reinterpret_cast<const float4*>(blk + static_cast<long long>(r) * lda + cq * 4);
+    Ls[r * LDD + cq * 4 + 0] = v.x;
+    Ls[r * LDD + cq * 4 + 1] = v.y;
+    Ls[r * LDD + cq * 4 + 2] = v.z;
+    Ls[r * LDD + cq * 4 + 3] = v.w;
+  }
+  __syncthreads();
+  // right-looking Cholesky on the lower triangle
+  for (int j = 0; j < TS; ++j) {
+    const float piv = Ls[j * LDD + j];
+    if (tid == 0 && !(piv > 0.f)) atomicCAS(info, 0, k * TS + j + 1);
+    const float d = sqrtf(fmaxf(piv, 1e-30f));
+    const float inv = 1.f / d;
+    __syncthreads();
+    for (int i = j + tid; i < TS; i += 256) Ls[i * LDD + j] = (i == j) ? d : Ls[i * LDD + j] * inv;
+    __syncthreads();
+    // trailing: A[i][c] -= L[i][j] L[c][j] for j < c <= i
+    const int rem = TS - 1 - j;
+    for (int e = tid; e < rem * rem; e += 256) {
+      const int i = j + 1 + e / rem, c = j + 1 + e % rem;
+      if (c <= i) Ls[i * LDD + c] = fmaf(-Ls[i * LDD + j], Ls[c * LDD + j], Ls[i * LDD + c]);
+    }
+    __syncthreads();
+  }
+  // inverse: column c of X = L^-1 by forward substitution, one thread per column
+  if (tid < TS) {
+    const int c = tid;
+    for (int i = 0; i < c; ++i) Xs[i * LDD + c] = 0.f;
+    Xs[c * LDD + c] = 1.f / Ls[c * LDD + c];
+    for (int i = c + 1; i < TS; ++i) {
+      float s0 = 0.f, s1 = 0.f;
+      int kk = c;
+      for (; kk + 1 < i; kk += 2) {
+        s0 = fmaf(Ls[i * LDD + kk], Xs[kk * LDD + c], s0);
+        s1 = fmaf(Ls[i * LDD + kk + 1], Xs[(kk + 1) * LDD + c], s1);
+      }
+      if (kk < i) s0 = fmaf(Ls[i * LDD + kk], Xs[kk * LDD + c], s0);
+      Xs[i * LDD + c] = -(s0 + s1) / Ls[i * LDD + i];
+    }
+  }
+  __syncthreads();
+  float* inv_out = invdiag + static_cast<long long>(k) * TS * TS;
+  for (int idx = tid; idx < TS * TS; idx += 256) {
+    const int r = idx >> 7, c = idx & 127;
+    blk[static_cast<long long>(r) * lda + c] = (c <= r) ? Ls[r * LDD + c] : 0.f;
+    inv_out[idx] = Xs[r * LDD + c];
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// block triangular solves
+// --------------------------------------------------------------------------------------------
+// out[128 x DP] = op(T)[128x128] * x[128 x DP]; thread t owns row t%128 and half of the columns.
+template <int DP, bool TRANS>
+__device__ __forceinline__ void tile_times_rhs(const float* Ts, const float* xs, float (&acc)[DP / 2]) {
+  const int o = threadIdx.x & 127;
+  const int c0 = (threadIdx.x >> 7) * (DP / 2);
+#pragma unroll
+  for (int c = 0; c < DP / 2; ++c) acc[c] = 0.f;
+#pragma unroll 4
+  for (int l = 0; l < TS; ++l) {
+    const float t = TRANS ? Ts[l * LDD + o] : Ts[o * LDD + l];
+#pragma unroll
+    for (int c = 0; c < DP / 2; ++c) acc[c] = fmaf(t, xs[l * DP + c0 + c], acc[c]);
+  }
+}
+
+__device__ __forceinline__ void load_tile_128(const float* __restrict__ src, long long ld, float* Ts) {
+  for (int idx = threadIdx.x; idx < TS * TS / 4; idx += 256) {
+    const int r = idx >> 5, cq = idx & 31;
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(src + static_cast<long long>(r) * ld + cq * 4));
+    Ts[r * LDD + cq * 4 + 0] = v.x;
+    Ts[r * LDD + cq * 4 + 1] = v.y;
+    Ts[r * LDD + cq * 4 + 2] = v.z;
+    Ts[r * LDD + cq * 4 + 3] = v.w;
+  }
+}
+
+// Forward step k (TRANS = false): CTA i = k + blockIdx.x:  b_i -= L(i, k-1) x_{k-1};  CTA i == k then
+// solves x_k = inv(L_kk) b_k.  Backward step k (TRANS = true): CTA j = blockIdx.x <= k:
+// b_j -= L(k+1, j)^T x_{k+1};  CTA j == k then solves x_k = inv(L_kk)^T b_k.
+template <int DP, bool TRANS>
+__global__ void __launch_bounds__(256)
+trsm_step_kernel(const float* __restrict__ L, long long ldl, const float* __restrict__ invdiag,
+                 float* __restrict__ Bm, int k, int nblk) {
+  extern __shared__ float tsm[];
+  float* Ts = tsm;              // [128][129]
+  float* xs = tsm + TS * LDD;   // [128][DP]
+  const int blk = TRANS ? static_cast<int>(blockIdx.x) : k + static_cast<int>(blockIdx.x);
+  const int src = TRANS ? k + 1 : k - 1;  // block whose solution is being eliminated
+  const bool has_update = TRANS ? (k + 1 < nblk) : (k > 0);
+  const int o = threadIdx.x & 127;
+  const int c0 = (threadIdx.x >> 7) * (DP / 2);
+  float* brow = Bm + (static_cast<long long>(blk) * TS + o) * DP + c0;
+  float bval[DP / 2];
+#pragma unroll
+  for (int c = 0; c < DP / 2; ++c) bval[c] = brow[c];
+
+  if (has_update) {
+    const float* tile = TRANS ? L + static_cast<long long>(src) * TS * ldl + static_cast<long long>(blk) * TS
+                              : L + static_cast<long long>(blk) * TS * ldl + static_cast<long long>(src) * TS;
+    load_tile_128(tile, ldl, Ts);
+    const float* xsrc = Bm + static_cast<long long>(src) * TS * DP;
+    for (int idx = threadIdx.x; idx < TS * DP; idx += 256) xs[idx] = xsrc[idx];
+    __syncthreads();
+    float acc[DP / 2];
+    tile_times_rhs<DP, TRANS>(Ts, xs, acc);
+#pragma unroll
+    for (int c = 0; c < DP / 2; ++c) bval[c] -= acc[c];
+  }
+  if (blk == k) {
+    __syncthreads();
+    load_tile_128(invdiag + static_cast<long long>(k) * TS * TS, TS, Ts);
+#pragma unroll
+    for (int c = 0; c < DP / 2; ++c) xs[o * DP + c0 + c] = bval[c];
+    __syncthreads();
+    float acc[DP / 2];
+    tile_times_rhs<DP, TRANS>(Ts, xs, acc);
+#pragma unroll
+    for (int c = 0; c < DP / 2; ++c) bval[c] = acc[c];
+  }
+#pragma unroll
+  for (int c = 0; c < DP / 2; ++c) brow[c] = bval[c];
+}
+
+// --------------------------------------------------------------------------------------------
+// small elementwise / reduction kernels
+// --------------------------------------------------------------------------------------------
+__global__ void add_diag_kernel(float* A, long long M, long long lda, float v) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < M) A[i * lda + i] += v;
+}
+
+__global__ void axpby_kernel(long long len, float a, const float* __restrict__ X, float b,
+                             float* __restrict__ Y) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += stride)
+    Y[i] = (b == 0.f) ? a * X[i] : fmaf(a, X[i], b * Y[i]);
+}
+
+// blockDim = (dp, rows_per_block): thread (c, ry) walks rows ry, ry + stride, ... of column c, so
+// a warp reads consecutive floats of the row-major M x dp array.
+constexpr int RED_THREADS = 512;
+
+__device__ __forceinline__ void block_column_reduce(float v, int dp, float* out) {
+  __shared__ float red[RED_THREADS];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  red[tid] = v;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float s = 0.f;
+    for (int r = 0; r < static_cast<int>(blockDim.y); ++r) s += red[r * dp + threadIdx.x];
+    atomicAdd(out + threadIdx.x, s);
+  }
+}
+
+__global__ void coldot_kernel(const float* __restrict__ P, const float* __restrict__ Q, long long M,
+                              int dp, float* __restrict__ out) {
+  float s = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.y;
+  for (long long r = static_cast<long long>(blockIdx.x) * blockDim.y + threadIdx.y; r < M; r += stride)
+    s = fmaf(P[r * dp + threadIdx.x], Q[r * dp + threadIdx.x], s);
+  block_column_reduce(s, dp, out);
+}
+
+__global__ void cg_update_kernel(long long M, int dp, const float* __restrict__ P,
+                                 const float* __restrict__ AP, float* __restrict__ X,
+                                 float* __restrict__ R, const float* __restrict__ rs_old,
+                                 const float* __restrict__ pAp, float eps, float* __restrict__ rs_new) {
+  const int c = threadIdx.x;
+  const float alpha = rs_old[c] / (pAp[c] + eps);
+  float s = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.y;
+  for (long long r = static_cast<long long>(blockIdx.x) * blockDim.y + threadIdx.y; r < M; r += stride) {
+    const long long i = r * dp + c;
+    X[i] = fmaf(alpha, P[i], X[i]);
+    if (AP != nullptr) {
+      const float rv = fmaf(-alpha, AP[i], R[i]);
+      R[i] = rv;
+      s = fmaf(rv, rv, s);
+    }
+  }
+  if (AP != nullptr) block_column_reduce(s, dp, rs_new);
+}
+
+__global__ void cg_direction_kernel(long long M, int dp, const float* __restrict__ R,
+                                    float* __restrict__ P, const float* __restrict__ rs_new,
+                                    const float* __restrict__ rs_old) {
+  const int c = threadIdx.x;
+  const float beta = rs_new[c] / rs_old[c];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.y;
+  for (long long r = static_cast<long long>(blockIdx.x) * blockDim.y + threadIdx.y; r < M; r += stride) {
+    const long long i = r * dp + c;
+    P[i] = fmaf(beta, P[i], R[i]);
+  }
+}
+
+static int red_grid(long long M, int rows_per_block) {
+  long long g = ceil_div(M, static_cast<long long>(rows_per_block) * 4);
+  if (g < 1) g = 1;
+  if (g > 592) g = 592;
+  return static_cast<int>(g);
+}
+
+template <int DP>
+static int trsm_launch(cudaStream_t st, const float* L, long long M, long long ldl, const float* invdiag,
+                       float* B, int transpose) {
+  const int nblk = static_cast<int>(M / TS);
+  const int smem = (TS * LDD + TS * DP) * static_cast<int>(sizeof(float));
+  if (transpose) {
+    auto kern = trsm_step_kernel<DP, true>;
+    SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int k = nblk - 1; k >= 0; --k) kern<<<k + 1, 256, smem, st>>>(L, ldl, invdiag, B, k, nblk);
+  } else {
+    auto kern = trsm_step_kernel<DP, false>;
+    SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int k = 0; k < nblk; ++k) kern<<<nblk - k, 256, smem, st>>>(L, ldl, invdiag, B, k, nblk);
+  }
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace la
+}  // namespace sab
+
+using namespace sab;
+using namespace sab::la;
+
+#define SAB_REQUIRE_MAT(M, ld, ptr)                                                                    \
+  SAB_REQUIRE((M) > 0 && (M) % TS == 0 && (ld) >= (M) && (ld) % 4 == 0 &&                              \
+                  (reinterpret_cast<uintptr_t>(ptr) & 15) == 0,                                       \
+              "matrix order must be a positive multiple of 128 with ld %% 4 == 0 and 16-byte aligned " \
+              "storage (M=%lld ld=%lld)",                                                             \
+              (long long)(M), (long long)(ld))
+
+extern "C" int sa_potrf(void* stream, float* A, int64_t M, int64_t lda, float* invdiag, int* info) {
+  SAB_REQUIRE_MAT(M, lda, A);
+  SAB_REQUIRE(invdiag != nullptr && info != nullptr, "invdiag / info must not be NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nblk = static_cast<int>(M / TS);
+  const int dsmem = 2 * TS * LDD * static_cast<int>(sizeof(float));
+  SAB_CHECK_CUDA(cudaFuncSetAttribute(diag_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dsmem));
+  SAB_CHECK_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+  for (int k = 0; k < nblk; ++k) {
+    diag_factor_kernel<<<1, 256, dsmem, st>>>(A, lda, k, invdiag, info);
+    const int rem = nblk - k - 1;
+    if (rem > 0) {
+      sgemm_kernel<MODE_PANEL><<<rem, 256, 0, st>>>(A, lda, invdiag + static_cast<long long>(k) * TS * TS,
+                                                    TS, k, nblk, 0.f, 0.f);
+      sgemm_kernel<MODE_SYRK><<<rem * (rem + 1) / 2, 256, 0, st>>>(A, lda, nullptr, 0, k, nblk, 0.f, 0.f);
+    }
+  }
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sa_ltl(void* stream, const float* L, int64_t M, int64_t ldl, float* G, int64_t ldg,
+                      float alpha, float beta) {
+  SAB_REQUIRE_MAT(M, ldl, L);
+  SAB_REQUIRE_MAT(M, ldg, G);
+  SAB_REQUIRE(L != G, "sa_ltl is out of place");
+  const int nblk = static_cast<int>(M / TS);
+  SAB_REQUIRE(nblk <= 2048, "matrix order %lld too large", (long long)M);
+  sgemm_kernel<MODE_LTL><<<nblk * (nblk + 1) / 2, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      G, ldg, L, ldl, 0, nblk, alpha, beta);
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sa_add_diag(void* stream, float* A, int64_t M, int64_t lda, float value) {
+  SAB_REQUIRE(M >= 0 && lda >= M, "bad shape");
+  if (M == 0) return 0;
+  add_diag_kernel<<<static_cast<int>(ceil_div(M, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      A, M, lda, value);
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sa_trsm(void* stream, const float* L, int64_t M, int64_t ldl, const float* invdiag,
+                       float* B, int dp, int transpose) {
+  SAB_REQUIRE_MAT(M, ldl, L);
+  SAB_REQUIRE(invdiag != nullptr && B != nullptr, "NULL operand");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dp) {
+    case 4: return trsm_launch<4>(st, L, M, ldl, invdiag, B, transpose);
+    case 8: return trsm_launch<8>(st, L, M, ldl, invdiag, B, transpose);
+    case 12: return trsm_launch<12>(st, L, M, ldl, invdiag, B, transpose);
+    case 16: return trsm_launch<16>(st, L, M, ldl, invdiag, B, transpose);
+    case 20: return trsm_launch<20>(st, L, M, ldl, invdiag, B, transpose);
+    case 24: return trsm_launch<24>(st, L, M, ldl, invdiag, B, transpose);
+    case 28: return trsm_launch<28>(st, L, M, ldl, invdiag, B, transpose);
+    case 32: return trsm_launch<32>(st, L, M, ldl, invdiag, B, transpose);
+  }
+  set_error("dp must be a multiple of 4 in [4, 32], got %d", dp);
+  return 2;
+}
+
+#define SAB_REQUIRE_VEC(M, dp) \
+  SAB_REQUIRE((M) > 0 && (dp) >= 1 && (dp) <= 32, "bad vector shape M=%lld dp=%d", (long long)(M), (dp))
+
+extern "C" int sa_coldot(void* stream, const float* P, const float* Q, int64_t M, int dp, float* out) {
+  SAB_REQUIRE_VEC(M, dp);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SAB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * dp, st));
+  const int rows = RED_THREADS / dp;
+  coldot_kernel<<<red_grid(M, rows), dim3(dp, rows), 0, st>>>(P, Q, M, dp, out);
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sa_cg_update(void* stream, int64_t M, int dp, const float* P, const float* AP, float* X,
+                            float* R, const float* rs_old, const float* pAp, float eps, float* rs_new) {
+  SAB_REQUIRE_VEC(M, dp);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (AP != nullptr) SAB_CHECK_CUDA(cudaMemsetAsync(rs_new, 0, sizeof(float) * dp, st));
+  const int rows = RED_THREADS / dp;
+  cg_update_kernel<<<red_grid(M, rows), dim3(dp, rows), 0, st>>>(M, dp, P, AP, X, R, rs_old, pAp, eps, rs_new);
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sa_cg_direction(void* stream, int64_t M, int dp, const float* R, float* P,
+                               const float* rs_new, const float* rs_old) {
+  SAB_REQUIRE_VEC(M, dp);
+  const int rows = RED_THREADS / dp;
+  cg_direction_kernel<<<red_grid(M, rows), dim3(dp, rows), 0, static_cast<cudaStream_t>(stream)>>>(
+      M, dp, R, P, rs_new, rs_old);
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sa_axpby(void* stream, int64_t len, float a, const float* X, float b, float* Y) {
+  SAB_REQUIRE(len >= 0, "negative length");
+  if (len == 0) return 0;
+  long long g = ceil_div(len, 256 * 4);
+  if (g > 1184) g = 1184;
+  axpby_kernel<<<static_cast<int>(g), 256, 0, static_cast<cudaStream_t>(stream)>>>(len, a, X, b, Y);
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
