@@ -128,8 +128,6 @@ def prep(X: torch.Tensor, shift: torch.Tensor | None, scale: torch.Tensor | None
         dptr, nptr = data.data_ptr(), norms.data_ptr()
     else:
         # fill rows [row_offset, row_offset + n) of an existing buffer (chunked staging)
-        if row_offset % NORM_PAD and row_offset + n != out.n:
-            pass
         dptr = out.data.data_ptr() + row_offset * out.p_pad * 2
         nptr = out.norms.data_ptr() + row_offset * 4
         last = row_offset + n == out.n

@@ -406,7 +406,8 @@ __global__ void cg_direction_kernel(long long M, int dp, const float* __restrict
                                     float* __restrict__ P, const float* __restrict__ rs_new,
                                     const float* __restrict__ rs_old) {
   const int c = threadIdx.x;
-  const float beta = rs_new[c] / rs_old[c];
+  const float ro = rs_old[c];
+  const float beta = ro > 0.f ? rs_new[c] / ro : 0.f;  // padded / exactly converged columns
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.y;
   for (long long r = static_cast<long long>(blockIdx.x) * blockDim.y + threadIdx.y; r < M; r += stride) {
     const long long i = r * dp + c;

@@ -1,0 +1,158 @@
+"""
+Device engine: the thin layer between the host algorithms (solver.py, falkon/) and the C ABI.
+
+`CudaOps` is the ONLY compute backend the package ships.  It owns host<->device staging (pinned,
+chunked, never writing into the caller's tensors -- the reference hands over read-only memmap-backed
+tensors, /root/reference/sobolev_alignment/sobolev_alignment.py:613-616,922-925) and forwards every
+numerical operation to libsobolev_b200.so.  The host algorithms are written against this small
+interface so that the multi-rank host logic can be exercised on CPU by the test-suite with a
+stand-in defined under tests/ (never importable from here).
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _native as nat
+
+
+class KernelSpec:
+    """Kernel family + length-scale, resolved to what the CUDA epilogue needs."""
+
+    __slots__ = ("family", "kid", "sigma", "sigma_vec")
+
+    def __init__(self, family: str, sigma):
+        if family not in nat.KERNEL_IDS:
+            raise KeyError(family)
+        self.family = family
+        self.kid = nat.KERNEL_IDS[family]
+        if torch.is_tensor(sigma) and sigma.numel() > 1:
+            self.sigma = None
+            self.sigma_vec = sigma.detach().to(torch.float32).flatten().cpu()
+        else:
+            self.sigma = float(sigma.item() if torch.is_tensor(sigma) else sigma)
+            self.sigma_vec = None
+            if not self.sigma > 0:
+                raise ValueError("sigma must be positive")
+
+    def kscale(self, gscale: float) -> float:
+        """Constant applied to the distance between PREPARED rows (which carry the factor gscale)."""
+        s = 1.0 if self.sigma is None else self.sigma
+        if self.family == "gaussian":
+            return 1.0 / (2.0 * s * s * gscale * gscale)
+        return 1.0 / (s * gscale)
+
+
+class Frame:
+    """Affine map applied to rows before rounding to fp16: (x - shift) * scale * gscale."""
+
+    __slots__ = ("shift", "scale", "gscale")
+
+    def __init__(self, shift, scale, gscale):
+        self.shift, self.scale, self.gscale = shift, scale, gscale
+
+
+class CudaOps:
+    name = "cuda"
+
+    def __init__(self, device=None, stage_rows: int = 65536):
+        if not torch.cuda.is_available():
+            raise nat.NativeLibraryError(
+                "sobolev_alignment_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        nat.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.stage_rows = int(stage_rows)
+        self._pinned = None
+
+    # ------------------------------------------------------------------ memory plumbing
+    def zeros(self, *shape, dtype=torch.float32):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    def empty(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def to_device(self, t: torch.Tensor) -> torch.Tensor:
+        """fp32 contiguous copy on the device (no-op when already there)."""
+        if t.is_cuda:
+            return t.to(device=self.device, dtype=torch.float32).contiguous()
+        return t.to(torch.float32).contiguous().to(self.device, non_blocking=False)
+
+    def to_host(self, t: torch.Tensor) -> torch.Tensor:
+        return t.detach().to("cpu")
+
+    # ------------------------------------------------------------------ frames
+    def make_frame(self, ref_rows: torch.Tensor, spec: KernelSpec) -> Frame:
+        """
+        Centre on the column mean of `ref_rows` (distances are translation invariant; centring keeps
+        |x|^2 small so |a|^2+|b|^2-2ab cancels less) and pick a power-of-two gain that puts the
+        centred rows at unit rms per feature, well inside fp16's normal range.
+        """
+        ref = ref_rows.to(device=self.device, dtype=torch.float32)
+        shift = ref.mean(0).contiguous()
+        scale = None
+        centred = ref - shift
+        if spec.sigma_vec is not None:
+            scale = (1.0 / spec.sigma_vec).to(self.device).contiguous()
+            centred = centred * scale
+        rms = float(centred.pow(2).mean().sqrt())
+        gscale = 1.0 if not (rms > 0 and math.isfinite(rms)) else 2.0 ** round(-math.log2(rms))
+        return Frame(shift, scale, gscale)
+
+    # ------------------------------------------------------------------ operand preparation
+    def prepare(self, X: torch.Tensor, frame: Frame) -> nat.Prepared:
+        """Rows of X (CPU or CUDA, any float dtype) -> prepared fp16 operand resident on the device."""
+        n, p = X.shape
+        if X.is_cuda:
+            Xd = X if X.dtype == torch.float32 and X.stride(1) == 1 else X.float().contiguous()
+            return nat.prep(Xd, frame.shift, frame.scale, frame.gscale)
+        out = nat.alloc_prepared(n, p, self.device)
+        if n == 0:
+            return out
+        rows = max(1, min(self.stage_rows, n))
+        if self._pinned is None or self._pinned[0].shape[1] != p or self._pinned[0].shape[0] < rows:
+            self._pinned = [torch.empty(rows, p, dtype=torch.float32).pin_memory() for _ in range(2)]
+        dev_bufs = [torch.empty(rows, p, dtype=torch.float32, device=self.device) for _ in range(2)]
+        events = [None, None]
+        stream = torch.cuda.current_stream(self.device)
+        for i, s in enumerate(range(0, n, rows)):
+            e = min(n, s + rows)
+            b = i & 1
+            if events[b] is not None:
+                events[b].synchronize()  # the pinned buffer is free again
+            src = X[s:e]
+            if src.is_pinned() and src.dtype == torch.float32 and src.is_contiguous():
+                dev_bufs[b][: e - s].copy_(src, non_blocking=True)
+            else:
+                self._pinned[b][: e - s].copy_(src)  # never writes into the caller's (maybe memmap) data
+                dev_bufs[b][: e - s].copy_(self._pinned[b][: e - s], non_blocking=True)
+            nat.prep(dev_bufs[b][: e - s], frame.shift, frame.scale, frame.gscale, out=out, row_offset=s)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            events[b] = ev
+        return out
+
+    # ------------------------------------------------------------------ numerical operations
+    def kmv(self, spec: KernelSpec, frame: Frame, A, B, V, out, symmetric=False):
+        return nat.kmv(spec.kid, spec.kscale(frame.gscale), A, B, V, out, symmetric)
+
+    def kdense(self, spec: KernelSpec, frame: Frame, A, B, out, symmetric=False):
+        return nat.kdense(spec.kid, spec.kscale(frame.gscale), A, B, out, symmetric)
+
+    potrf = staticmethod(nat.potrf)
+    ltl = staticmethod(nat.ltl)
+    add_diag = staticmethod(nat.add_diag)
+    trsm = staticmethod(nat.trsm)
+    coldot = staticmethod(nat.coldot)
+    cg_update = staticmethod(nat.cg_update)
+    cg_direction = staticmethod(nat.cg_direction)
+    axpby = staticmethod(nat.axpby)
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.device)
+
+
+def pad_cols(d: int) -> int:
+    """Right-hand sides are padded to a multiple of 4 columns (128-bit shared-memory reads)."""
+    return max(4, nat.round_up(d, 4))

@@ -1,0 +1,254 @@
+"""
+FALKON host algorithm (Rudi, Carratino, Rosasco 2017, Alg. 1; Meanti et al. 2020) over the device
+engine.  This is the part of the third-party `falkon` package the reference reaches through
+`Falkon.fit` / `Falkon.predict` (/root/reference/sobolev_alignment/krr_approx.py:227,314); SURVEY
+section 3.1 lists the steps.
+
+    T = chol(K_MM + eps M I)  (upper)    stored as the lower factor L  = T^T
+    A = chol(T T^T / M + lambda I)       stored as the lower factor LA = A^T
+    rhs  = A^-T T^-T K_nM^T (Y / n)
+    BHB u = A^-T ( T^-T K_nM^T (K_nM T^-1 A^-1 u) / n + lambda A^-1 u )
+    beta = CG(BHB, rhs) ;  alpha = T^-1 A^-1 beta
+
+The two products with K_nM are two launches of the fused `kmv` kernel (K_nM is recomputed, never
+stored).  Rows of X may be sharded over ranks: each rank computes K_g^T (K_g z) for its rows and the
+M x d partial sums are all-reduced once per product pair; everything else is replicated and
+deterministic, so ranks stay bit-identical without a broadcast.
+"""
+
+from __future__ import annotations
+
+import time
+
+import torch
+
+from .engine import KernelSpec, pad_cols
+
+TILE = 128
+
+
+class Comm:
+    """Sum all-reduce over the ranks that hold row shards (identity for a single process)."""
+
+    def __init__(self, group=None, enabled: bool = False):
+        self.enabled = enabled
+        self.group = group
+        if enabled:
+            import torch.distributed as dist
+
+            self.dist = dist
+            self.world = dist.get_world_size(group)
+            self.rank = dist.get_rank(group)
+        else:
+            self.world, self.rank = 1, 0
+
+    def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        if self.enabled and self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def sum_int(self, v: int, device) -> int:
+        if not (self.enabled and self.world > 1):
+            return v
+        t = torch.tensor([v], dtype=torch.int64, device=device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return int(t.item())
+
+
+class Preconditioner:
+    """Lower Cholesky factors L (= T^T) and LA (= A^T) with their inverted diagonal blocks."""
+
+    def __init__(self, ops, spec: KernelSpec, frame, Cprep, penalty: float, pc_eps: float):
+        M = Cprep.n
+        Mp = (M + TILE - 1) // TILE * TILE
+        self.ops, self.M, self.Mp = ops, M, Mp
+        nblk = Mp // TILE
+        # K_MM, padded with an identity block (leaves factors and solves of the leading block unchanged)
+        K = ops.zeros(Mp, Mp)
+        ops.kdense(spec, frame, Cprep, Cprep, K, symmetric=True)
+        if Mp > M:
+            K.diagonal()[M:] = 1.0
+        ops.add_diag(K, M, pc_eps * M)
+        self.L = K
+        self.L_inv = ops.empty(nblk, TILE, TILE)
+        self.info = ops.zeros(2, dtype=torch.int32)
+        ops.potrf(self.L, self.L_inv, self.info[0:1])
+        # A A^T ... : G = L^T L / M + lambda I  (= T T^T / M + lambda I), then its Cholesky factor
+        G = ops.empty(Mp, Mp)
+        ops.ltl(self.L, G, 1.0 / M, penalty)
+        self.LA = G
+        self.LA_inv = ops.empty(nblk, TILE, TILE)
+        ops.potrf(self.LA, self.LA_inv, self.info[1:2])
+
+    def check(self):
+        info = self.ops.to_host(self.info).tolist()
+        if info[0] or info[1]:
+            which = "K_MM + eps*M*I" if info[0] else "T T^T / M + lambda*I"
+            raise RuntimeError(
+                f"Cholesky of {which} failed at pivot {max(info) - 1}: matrix not positive definite "
+                "(increase penalization / check for duplicated centres)")
+
+    # in-place solves on [Mp x dp] buffers
+    def invT(self, v):
+        return self.ops.trsm(self.L, self.L_inv, v, True)
+
+    def invTt(self, v):
+        return self.ops.trsm(self.L, self.L_inv, v, False)
+
+    def invA(self, v):
+        return self.ops.trsm(self.LA, self.LA_inv, v, True)
+
+    def invAt(self, v):
+        return self.ops.trsm(self.LA, self.LA_inv, v, False)
+
+
+class FalkonSolver:
+    def __init__(self, ops, spec: KernelSpec, penalty: float, maxiter: int = 20, pc_eps: float = 1e-5,
+                 cg_eps: float = 1e-7, cg_tol: float = 1e-7, full_grad_every: int = 10, comm: Comm | None = None):
+        self.ops, self.spec = ops, spec
+        self.penalty, self.maxiter = float(penalty), int(maxiter)
+        self.pc_eps, self.cg_eps, self.cg_tol = float(pc_eps), float(cg_eps), float(cg_tol)
+        self.full_grad_every = int(full_grad_every)
+        self.comm = comm or Comm()
+        self.times = {}
+        self.residuals = []
+        self.n_iter_ = 0
+        self.n_kmv_ = 0
+
+    # ------------------------------------------------------------------ products with K_nM
+    def _knm_t_knm(self, z, out):
+        """out[:M] = sum over local rows of K_g^T (K_g z[:M]), all-reduced over ranks."""
+        ops, M = self.ops, self.M
+        self.t_buf.zero_()
+        ops.kmv(self.spec, self.frame, self.Xprep, self.Cprep, z[:M], self.t_buf)
+        out.zero_()
+        ops.kmv(self.spec, self.frame, self.Cprep, self.Xprep, self.t_buf, out[:M])
+        self.n_kmv_ += 2
+        self.comm.all_reduce(out)
+        return out
+
+    def _bhb(self, u, out):
+        """out = BHB u  (u is left untouched; w1/w2 are scratch)."""
+        ops, pre = self.ops, self.pre
+        v = self.w1
+        v.copy_(u)
+        pre.invA(v)                       # v = A^-1 u
+        z = self.w2
+        z.copy_(v)
+        pre.invT(z)                       # z = T^-1 v
+        self._knm_t_knm(z, out)           # out = K_nM^T K_nM z
+        ops.axpby(1.0 / self.n_total, out, 0.0, out)   # out /= n
+        pre.invTt(out)                    # T^-T (. / n)
+        ops.axpby(self.penalty, v, 1.0, out)  # + lambda v
+        pre.invAt(out)
+        return out
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, X, Y, centres, n_total: int | None = None):
+        """
+        X [n x p], Y [n x d]: this rank's rows (CPU or CUDA).  centres [M x p]: identical on all ranks.
+        Returns alpha [M x d] (float32, on the engine's device).
+        """
+        ops = self.ops
+        t0 = time.perf_counter()
+        n, d = Y.shape
+        dp = pad_cols(d)
+        if dp > 32:
+            raise NotImplementedError("more than 32 output columns: split Y column-wise")
+        self.n_total = int(n_total) if n_total is not None else self.comm.sum_int(n, ops.device)
+        C = ops.to_device(centres)
+        M = self.M = C.shape[0]
+        self.frame = ops.make_frame(C, self.spec)
+        self.Cprep = ops.prepare(C, self.frame)
+        del C
+        self.pre = pre = Preconditioner(ops, self.spec, self.frame, self.Cprep, self.penalty, self.pc_eps)
+        Mp = pre.Mp
+        ops.synchronize()
+        self.times["preconditioner"] = time.perf_counter() - t0
+
+        t1 = time.perf_counter()
+        self.Xprep = ops.prepare(X, self.frame)
+        Yd = ops.zeros(n, dp)
+        Yd[:, :d] = ops.to_device(Y)
+        ops.synchronize()
+        self.times["stage_inputs"] = time.perf_counter() - t1
+
+        t2 = time.perf_counter()
+        self.t_buf = ops.empty(n, dp)
+        self.w1, self.w2 = ops.zeros(Mp, dp), ops.zeros(Mp, dp)
+        B = ops.zeros(Mp, dp)
+        # rhs = A^-T T^-T K_nM^T (Y / n)
+        ops.axpby(1.0 / self.n_total, Yd, 0.0, Yd)     # Y / n
+        ops.kmv(self.spec, self.frame, self.Cprep, self.Xprep, Yd, B[:M])
+        self.n_kmv_ += 1
+        self.comm.all_reduce(B)
+        del Yd
+        pre.invTt(B)
+        pre.invAt(B)
+        pre.check()
+
+        beta = self._conjugate_gradient(B, Mp, dp)
+        pre.invA(beta)
+        pre.invT(beta)
+        ops.synchronize()
+        self.times["cg"] = time.perf_counter() - t2
+        self.times["fit"] = time.perf_counter() - t0
+        return beta[:M, :d].contiguous()
+
+    def _conjugate_gradient(self, B, Mp, dp):
+        ops = self.ops
+        X = ops.zeros(Mp, dp)
+        R = B.clone()
+        P = B.clone()
+        AP = ops.zeros(Mp, dp)
+        rs_old, rs_new, pAp = ops.empty(dp), ops.empty(dp), ops.empty(dp)
+        ops.coldot(R, R, rs_old)
+        self.residuals = []
+        for it in range(self.maxiter):
+            self._bhb(P, AP)
+            ops.coldot(P, AP, pAp)
+            if (it + 1) % self.full_grad_every == 0:
+                ops.cg_update(P, None, X, None, rs_old, pAp, self.cg_eps, None)   # X += alpha P
+                self._bhb(X, R)                                                  # R = B - BHB X
+                ops.axpby(1.0, B, -1.0, R)
+                ops.coldot(R, R, rs_new)
+            else:
+                ops.cg_update(P, AP, X, R, rs_old, pAp, self.cg_eps, rs_new)
+            self.n_iter_ = it + 1
+            res = float(rs_new.max().sqrt())  # one small D2H read per iteration, as Falkon does
+            self.residuals.append(res)
+            if res < self.cg_tol:
+                break
+            ops.cg_direction(R, P, rs_new, rs_old)
+            rs_old, rs_new = rs_new, rs_old
+        return X
+
+    # ------------------------------------------------------------------ release
+    def release(self):
+        for name in ("pre", "Xprep", "t_buf", "w1", "w2"):
+            if hasattr(self, name):
+                delattr(self, name)
+
+
+class Predictor:
+    """K(X, C) alpha with the centres and coefficients resident on the device."""
+
+    def __init__(self, ops, spec: KernelSpec, centres: torch.Tensor, alpha: torch.Tensor):
+        self.ops, self.spec = ops, spec
+        C = ops.to_device(centres)
+        self.frame = ops.make_frame(C, spec)
+        self.Cprep = ops.prepare(C, self.frame)
+        self.d = alpha.shape[1]
+        self.dp = pad_cols(self.d)
+        if self.dp > 32:
+            raise NotImplementedError("more than 32 output columns")
+        self.alpha = ops.zeros(C.shape[0], self.dp)
+        self.alpha[:, : self.d] = ops.to_device(alpha)
+
+    def predict(self, X: torch.Tensor, row_chunk: int = 262144) -> torch.Tensor:
+        ops = self.ops
+        out = ops.zeros(X.shape[0], self.dp)
+        for s in range(0, X.shape[0], row_chunk):
+            Xp = ops.prepare(X[s : s + row_chunk], self.frame)
+            ops.kmv(self.spec, self.frame, Xp, self.Cprep, self.alpha, out[s : s + row_chunk])
+        return out[:, : self.d]

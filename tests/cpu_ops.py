@@ -1,0 +1,95 @@
+"""
+TEST-ONLY stand-in for `sobolev_alignment_b200.engine.CudaOps`: same interface, torch-CPU float64
+arithmetic taken from the oracle.  It exists so the HOST logic (FALKON driver, row sharding, gloo
+all-reduce, API plumbing) can be exercised without a GPU.  It lives under tests/ and is never
+importable from the product package.
+"""
+
+import math
+
+import torch
+
+from oracle import falkon_oracle as fo
+
+_FAMILY = {"gaussian": ("gaussian", None), "laplacian": ("laplacian", None),
+           "matern15": ("matern", 1.5), "matern25": ("matern", 2.5)}
+
+
+class _Rows:
+    def __init__(self, data):
+        self.data, self.n, self.p = data, data.shape[0], data.shape[1]
+
+
+class CpuOps:
+    name = "cpu-oracle"
+
+    def __init__(self, device=None, stage_rows=65536):
+        self.device = torch.device("cpu")
+
+    def zeros(self, *shape, dtype=torch.float32):
+        return torch.zeros(*shape, dtype=torch.float64 if dtype == torch.float32 else dtype)
+
+    def empty(self, *shape, dtype=torch.float32):
+        return self.zeros(*shape, dtype=dtype)
+
+    def to_device(self, t):
+        return t.detach().to(torch.float64).contiguous()
+
+    def to_host(self, t):
+        return t
+
+    def make_frame(self, ref_rows, spec):
+        return None
+
+    def prepare(self, X, frame):
+        return _Rows(X.detach().to(torch.float64))
+
+    def _k(self, spec, A, B):
+        fam, nu = _FAMILY[spec.family]
+        return fo.kernel_matrix(A.data, B.data, fam, spec.sigma, nu, direct=False)
+
+    def kmv(self, spec, frame, A, B, V, out, symmetric=False):
+        out += self._k(spec, A, B) @ V
+        return out
+
+    def kdense(self, spec, frame, A, B, out, symmetric=False):
+        out[: A.n, : B.n] = self._k(spec, A, B)
+        return out
+
+    def potrf(self, A, invdiag, info):
+        L = torch.linalg.cholesky(torch.tril(A) + torch.tril(A, -1).T)
+        A.copy_(L)
+
+    def ltl(self, L, G, alpha, beta):
+        Lt = torch.tril(L)
+        G.copy_(alpha * (Lt.T @ Lt) + beta * torch.eye(L.shape[0], dtype=L.dtype))
+
+    def add_diag(self, A, m, value):
+        A.diagonal()[:m] += value
+
+    def trsm(self, L, invdiag, B, transpose):
+        Lt = torch.tril(L)
+        B.copy_(torch.linalg.solve_triangular(Lt.T if transpose else Lt, B, upper=bool(transpose)))
+        return B
+
+    def coldot(self, P, Q, out):
+        out.copy_((P * Q).sum(0))
+        return out
+
+    def cg_update(self, P, AP, X, R, rs_old, pAp, eps, rs_new):
+        alpha = rs_old / (pAp + eps)
+        X += P * alpha[None, :]
+        if AP is not None:
+            R -= AP * alpha[None, :]
+            rs_new.copy_((R * R).sum(0))
+
+    def cg_direction(self, R, P, rs_new, rs_old):
+        beta = torch.where(rs_old > 0, rs_new / rs_old, torch.zeros_like(rs_old))
+        P.copy_(R + P * beta[None, :])
+
+    def axpby(self, a, X, b, Y):
+        Y.copy_(a * X + b * Y)
+        return Y
+
+    def synchronize(self):
+        pass

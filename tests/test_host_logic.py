@@ -1,0 +1,229 @@
+"""
+CPU: host-side logic (FALKON driver, API plumbing, row sharding over gloo) with the test-only
+stand-in engine of tests/cpu_ops.py.  Numerics of the CUDA kernels are NOT tested here (see -m gpu).
+"""
+import math
+import os
+import pickle
+import socket
+import warnings
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import falkon_oracle as fo
+from sobolev_alignment_b200 import KRRApprox, MultiKRRApprox, mat_inv_sqrt
+from sobolev_alignment_b200.engine import KernelSpec, pad_cols
+from sobolev_alignment_b200.falkon import Falkon, FalkonOptions
+from sobolev_alignment_b200.falkon import models as falkon_models
+from sobolev_alignment_b200.falkon.kernels import GaussianKernel, LaplacianKernel, MaternKernel
+from sobolev_alignment_b200.solver import Comm, FalkonSolver
+
+from conftest import krr_test_data, relerr
+from cpu_ops import CpuOps
+
+
+# ---------------------------------------------------------------------------- constructors / API
+def test_create_null_instance():
+    KRRApprox()
+
+
+def test_all_kernels_construct_under_both_methods():
+    for kernel in KRRApprox.sklearn_kernel:
+        KRRApprox(kernel=kernel, method="sklearn")
+    for kernel in KRRApprox.falkon_kernel:
+        clf = KRRApprox(kernel=kernel, method="falkon")
+        assert callable(clf.kernel_)
+
+
+def test_unknown_method_and_kernel_errors():
+    with pytest.raises(NotImplementedError):
+        KRRApprox(method="keops")
+    with pytest.raises(KeyError):
+        KRRApprox(method="falkon", kernel="polynomial", kernel_params={"sigma": 1})
+
+
+def test_matern_nu_mapping_and_validation():
+    assert MaternKernel(sigma=2.0, nu=0.5).spec().family == "laplacian"
+    assert MaternKernel(sigma=2.0, nu=1.5).spec().family == "matern15"
+    assert MaternKernel(sigma=2.0, nu=2.5).spec().family == "matern25"
+    assert MaternKernel(sigma=2.0, nu=np.inf).spec().family == "gaussian"
+    with pytest.raises(ValueError):
+        MaternKernel(sigma=2.0, nu=3.5)
+    assert GaussianKernel(sigma=2.0).spec().kscale(4.0) == pytest.approx(1 / (2 * 4 * 16))
+    assert LaplacianKernel(sigma=2.0).spec().kscale(4.0) == pytest.approx(1 / 8)
+
+
+def test_kernels_pickle_roundtrip():
+    for k in (GaussianKernel(sigma=3.0), LaplacianKernel(sigma=1.5), MaternKernel(sigma=2.0, nu=2.5)):
+        k2 = pickle.loads(pickle.dumps(k))
+        assert repr(k2) == repr(k)
+
+
+def test_falkon_options_accepts_model_selection_keys():
+    """krr_model_selection.py:55-64 passes these through KRRApprox(falkon_options=...)."""
+    opts = dict(never_store_kernel=True, min_cuda_iter_size_32=np.iinfo(np.int64).max,
+                min_cuda_iter_size_64=np.iinfo(np.int64).max, num_fmm_streams=6, max_cpu_mem=1e9, max_gpu_mem=1e9)
+    clf = KRRApprox(method="falkon", kernel="matern", kernel_params={"sigma": 1.0, "nu": np.inf},
+                    falkon_options=opts)
+    clf._setup_clf()
+    assert clf.ridge_clf_.options.num_fmm_streams == 6
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        FalkonOptions(no_such_option=1)
+        assert any("unknown option" in str(x.message) for x in w)
+
+
+def test_pad_cols():
+    assert [pad_cols(d) for d in (1, 4, 5, 10, 20, 32)] == [4, 4, 8, 12, 20, 32]
+
+
+def test_mat_inv_sqrt_matches_reference_definition():
+    rng = np.random.default_rng(1)
+    B = rng.standard_normal((7, 7))
+    M = B @ B.T
+    S = mat_inv_sqrt(M)
+    assert np.allclose(S, fo.mat_inv_sqrt(M), atol=1e-10)
+    assert np.allclose(S @ M @ S, np.eye(7), atol=1e-8)
+    # rank-deficient: small singular values are dropped, not inverted
+    M2 = B[:, :3] @ B[:, :3].T
+    assert np.linalg.matrix_rank(mat_inv_sqrt(M2)) == 3
+    assert np.allclose(mat_inv_sqrt(torch.tensor(M)), S)
+
+
+# ---------------------------------------------------------------------------- solver host logic
+def _fit_cpu(X, Y, C, family, sigma, lam, maxiter=20, comm=None, **kw):
+    solver = FalkonSolver(CpuOps(), KernelSpec(family, sigma), lam, maxiter, comm=comm, **kw)
+    return solver.fit(X, Y, C, n_total=None), solver
+
+
+@pytest.mark.parametrize("family,okernel,nu", [("laplacian", "laplacian", None), ("matern15", "matern", 1.5),
+                                               ("gaussian", "rbf", None)])
+def test_solver_matches_oracle_single_process(family, okernel, nu):
+    X, Xv, W, Y, Yv = krr_test_data(seed=4, n=700, p=30, d=5)
+    C = X[:130]          # M not a multiple of 128: exercises the identity padding of the preconditioner
+    sigma = float(np.sqrt(60))
+    alpha, solver = _fit_cpu(X, Y, C, family, sigma, 1e-4)
+    ref = fo.falkon_fit(X, Y, C, okernel, sigma, 1e-4, nu=nu)
+    assert alpha.shape == (130, 5)
+    assert relerr(alpha, ref) < 1e-6
+    assert solver.n_kmv_ == 1 + 2 * (solver.n_iter_ + solver.n_iter_ // 10)
+
+
+def test_solver_stops_on_tolerance():
+    X, Xv, W, Y, Yv = krr_test_data(seed=5, n=200, p=10, d=2)
+    # M = n and a negligible jitter: the preconditioner is exact, CG converges at once
+    alpha, solver = _fit_cpu(X, Y, X, "gaussian", 5.0, 1e-2, maxiter=50, pc_eps=1e-13, cg_eps=1e-15)
+    assert solver.n_iter_ < 10
+    assert solver.residuals[-1] < 1e-7
+
+
+def test_falkon_estimator_on_cpu_standin(monkeypatch, tmp_path):
+    monkeypatch.setattr(falkon_models, "CudaOps", CpuOps)
+    X, Xv, W, Y, Yv = krr_test_data(seed=6, n=500, p=20, d=3)
+    idx = np.sort(np.random.default_rng(0).choice(500, 100, replace=False))
+    clf = KRRApprox(method="falkon", kernel="matern", kernel_params={"sigma": 6.0, "nu": 1.5}, M=100,
+                    penalization=1e-4)
+    clf._setup_clf()
+    # same centres for oracle and solver: Falkon draws them from an unseeded host RNG
+    orig = Falkon._select_centres
+    monkeypatch.setattr(Falkon, "_select_centres", lambda self, n: idx)
+    clf.fit(X, Y)
+    monkeypatch.setattr(Falkon, "_select_centres", orig)
+    ref = fo.falkon_fit(X, Y, X[idx], "matern", 6.0, 1e-4, nu=1.5)
+    assert clf.sample_weights_.dtype == torch.float32 and not clf.sample_weights_.is_cuda
+    assert clf.sample_weights_.shape == (100, 3)
+    assert torch.equal(clf.anchors(), X[idx])
+    assert relerr(clf.sample_weights_, ref) < 1e-4
+    pred = clf.transform(Xv)
+    assert pred.shape == (50, 3) and pred.dtype == torch.float32
+    assert relerr(pred, fo.falkon_predict(Xv, X[idx], ref, "matern", 6.0, 1.5)) < 1e-4
+    # save / load: the estimator must predict from ASSIGNED ny_points_/alpha_ (krr_approx.py:402-404)
+    folder = str(tmp_path / "krr")
+    clf.save(folder)
+    for f in ("params.pkl", "sample_anchors.pt", "sample_weights.pt", "sample_anchors.csv", "sample_weights.csv"):
+        assert os.path.exists(os.path.join(folder, f))
+    clf2 = KRRApprox.load(folder)
+    assert clf2.method == "falkon" and clf2.M == 100
+    assert relerr(clf2.transform(Xv), pred) < 1e-6
+    assert np.allclose(np.loadtxt(os.path.join(folder, "sample_weights.csv")), clf.sample_weights_.numpy(), atol=1e-6)
+    # MultiKRRApprox is a pure consumer of the same surface
+    multi = MultiKRRApprox()
+    multi.add_clf(clf)
+    multi.add_clf(clf2)
+    multi.process_clfs()
+    assert multi.anchors().shape == (200, 20) and multi.sample_weights_.shape == (200, 3)
+    assert relerr(multi.transform(Xv), pred) < 1e-6
+
+
+def test_centre_selection_rules():
+    f = Falkon(kernel=GaussianKernel(1.0), penalty=1e-3, M=10, seed=3)
+    idx = f._select_centres(100)
+    assert len(idx) == 10 and len(set(idx.tolist())) == 10 and (np.diff(idx) > 0).all()
+    assert np.array_equal(idx, Falkon(kernel=GaussianKernel(1.0), penalty=1e-3, M=10, seed=3)._select_centres(100))
+    with warnings.catch_warnings(record=True):
+        warnings.simplefilter("always")
+        assert np.array_equal(Falkon(kernel=GaussianKernel(1.0), penalty=1e-3, M=500)._select_centres(20), np.arange(20))
+    explicit = Falkon(kernel=GaussianKernel(1.0), penalty=1e-3, M=3, center_selection=torch.tensor([5, 1, 9]))
+    assert explicit._select_centres(100).tolist() == [5, 1, 9]
+
+
+def test_sklearn_method_still_works():
+    """The reference's sklearn branch (tests/test_krr_approx.py:178-205,235-249) on the same logic."""
+    X, Xv, W, Y, Yv = krr_test_data(seed=7, n=400, p=30, d=4)
+    clf = KRRApprox(method="sklearn", kernel="matern", kernel_params={"length_scale": 30.0, "nu": 1.5},
+                    penalization=1e-4).fit(X, Y)
+    pred = clf.transform(Xv)
+    assert np.corrcoef(np.asarray(pred).ravel(), Yv.numpy().ravel())[0, 1] > 0.99
+    rec = clf.kernel_(Xv, X[clf.ridge_samples_idx_, :]).dot(clf.sample_weights_)
+    np.testing.assert_array_almost_equal(rec, pred, decimal=3)
+
+
+# ---------------------------------------------------------------------------- row sharding over gloo
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _rank_main(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        X, Xv, W, Y, Yv = krr_test_data(seed=8, n=601, p=24, d=3)     # 601 rows: ragged shards
+        bounds = np.linspace(0, X.shape[0], world + 1).astype(int)
+        Xl, Yl = X[bounds[rank]:bounds[rank + 1]], Y[bounds[rank]:bounds[rank + 1]]
+        falkon_models.CudaOps = CpuOps     # test-only engine swap inside this worker process
+        clf = Falkon(kernel=LaplacianKernel(sigma=7.0), penalty=1e-4, M=90, seed=5,
+                     options=FalkonOptions(row_sharded=True))
+        clf.fit(Xl, Yl)
+        pred = clf.predict(Xv)
+        torch.save({"alpha": clf.alpha_, "centres": clf.ny_points_, "pred": pred,
+                    "n_total": clf.solver_stats_["n_total"]}, os.path.join(out_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_fit_world2_gloo(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_rank_main, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(os.path.join(tmp_path, "rank0.pt"))
+    r1 = torch.load(os.path.join(tmp_path, "rank1.pt"))
+    assert r0["n_total"] == 601
+    # replicated state stays bit-identical across ranks
+    assert torch.equal(r0["alpha"], r1["alpha"]) and torch.equal(r0["centres"], r1["centres"])
+    X, Xv, W, Y, Yv = krr_test_data(seed=8, n=601, p=24, d=3)
+    idx = np.sort(np.random.default_rng(5).choice(601, size=90, replace=False))
+    assert relerr(r0["centres"], X[idx]) < 1e-7
+    ref = fo.falkon_fit(X, Y, X[idx], "laplacian", 7.0, 1e-4)
+    assert relerr(r0["alpha"], ref) < 1e-4
+    assert relerr(r0["pred"], fo.falkon_predict(Xv, X[idx], ref, "laplacian", 7.0)) < 1e-4
