@@ -28,6 +28,36 @@ class NativeLibraryError(RuntimeError):
     pass
 
 
+class LaunchStats:
+    """
+    Launch accounting for bench.py: `launches` counts the CUDA kernels this library enqueued; when
+    `time_kmv` is set every fused-kernel launch is bracketed by CUDA events on the launching stream.
+    """
+
+    def __init__(self):
+        self.reset()
+        self.time_kmv = False
+
+    def reset(self):
+        self.launches = 0
+        self.kmv_events = []   # (flops, start_event, end_event)
+        self.trsm_events = []  # (bytes, start_event, end_event)
+
+    def kmv_summary(self):
+        """(total algorithmic flops, total seconds, launches) over the recorded fused-kernel launches."""
+        fl = sum(f for f, _, _ in self.kmv_events)
+        ms = sum(a.elapsed_time(b) for _, a, b in self.kmv_events)
+        return fl, ms * 1e-3, len(self.kmv_events)
+
+    def trsm_summary(self):
+        by = sum(f for f, _, _ in self.trsm_events)
+        ms = sum(a.elapsed_time(b) for _, a, b in self.trsm_events)
+        return by, ms * 1e-3, len(self.trsm_events)
+
+
+STATS = LaunchStats()
+
+
 _lib = None
 
 _SIGNATURES = {
@@ -136,6 +166,7 @@ def prep(X: torch.Tensor, shift: torch.Tensor | None, scale: torch.Tensor | None
         return out
     _check(lib.sa_prep(_stream(), X.data_ptr(), n, p, X.stride(0), _ptr(shift), _ptr(scale),
                        float(gscale), dptr, out.p_pad, nptr, norms_len))
+    STATS.launches += 1
     return out
 
 
@@ -157,9 +188,18 @@ def kmv(kernel_id: int, kscale: float, A: Prepared, B: Prepared, V: torch.Tensor
         raise ValueError(f"shape mismatch: V {tuple(V.shape)}, out {tuple(out.shape)}, a={A.n}, b={B.n}")
     if A.p_pad != B.p_pad:
         raise ValueError("A and B were prepared with different feature counts")
+    ev = None
+    if STATS.time_kmv:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     _check(lib.sa_kmv(_stream(), kernel_id, float(kscale), A.data.data_ptr(), A.norms.data_ptr(), A.n,
                       A.p_pad, B.data.data_ptr(), B.norms.data_ptr(), B.n, B.p_pad, A.p_pad,
                       V.data_ptr(), dp, out.data_ptr(), int(symmetric)))
+    if ev is not None:
+        ev[1].record()
+        # algorithmic work: 2 a b p + 2 a b d, with the caller's p and padded d
+        STATS.kmv_events.append((2.0 * A.n * B.n * (A.p + dp), ev[0], ev[1]))
+    STATS.launches += 1
     return out
 
 
@@ -174,6 +214,7 @@ def kdense(kernel_id: int, kscale: float, A: Prepared, B: Prepared, out: torch.T
     _check(lib.sa_kdense(_stream(), kernel_id, float(kscale), A.data.data_ptr(), A.norms.data_ptr(), A.n,
                          A.p_pad, B.data.data_ptr(), B.norms.data_ptr(), B.n, B.p_pad, A.p_pad,
                          out.data_ptr(), out.stride(0), int(symmetric)))
+    STATS.launches += 1
     return out
 
 
@@ -182,6 +223,7 @@ def potrf(A: torch.Tensor, invdiag: torch.Tensor, info: torch.Tensor):
     _req(invdiag, torch.float32, "invdiag")
     _check(load().sa_potrf(_stream(), A.data_ptr(), A.shape[0], A.stride(0), invdiag.data_ptr(),
                            info.data_ptr()))
+    STATS.launches += 3 * (A.shape[0] // TILE) - 2
 
 
 def ltl(L: torch.Tensor, G: torch.Tensor, alpha: float, beta: float):
@@ -189,11 +231,13 @@ def ltl(L: torch.Tensor, G: torch.Tensor, alpha: float, beta: float):
     _req(G, torch.float32, "G")
     _check(load().sa_ltl(_stream(), L.data_ptr(), L.shape[0], L.stride(0), G.data_ptr(), G.stride(0),
                          float(alpha), float(beta)))
+    STATS.launches += 1
 
 
 def add_diag(A: torch.Tensor, m: int, value: float):
     _req(A, torch.float32, "A")
     _check(load().sa_add_diag(_stream(), A.data_ptr(), m, A.stride(0), float(value)))
+    STATS.launches += 1
 
 
 def trsm(L: torch.Tensor, invdiag: torch.Tensor, B: torch.Tensor, transpose: bool):
@@ -201,8 +245,17 @@ def trsm(L: torch.Tensor, invdiag: torch.Tensor, B: torch.Tensor, transpose: boo
     _req(B, torch.float32, "B")
     if B.shape[0] != L.shape[0]:
         raise ValueError("rhs rows must equal the (padded) matrix order")
+    ev = None
+    if STATS.time_kmv:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     _check(load().sa_trsm(_stream(), L.data_ptr(), L.shape[0], L.stride(0), invdiag.data_ptr(),
                           B.data_ptr(), B.shape[1], int(transpose)))
+    if ev is not None:
+        ev[1].record()
+        m = L.shape[0]
+        STATS.trsm_events.append((m * (m + TILE) / 2 * 4.0, ev[0], ev[1]))   # the triangle is read once
+    STATS.launches += L.shape[0] // TILE
     return B
 
 
@@ -210,6 +263,7 @@ def coldot(P: torch.Tensor, Q: torch.Tensor, out: torch.Tensor):
     _req(P, torch.float32, "P")
     _req(Q, torch.float32, "Q")
     _check(load().sa_coldot(_stream(), P.data_ptr(), Q.data_ptr(), P.shape[0], P.shape[1], out.data_ptr()))
+    STATS.launches += 1
     return out
 
 
@@ -217,11 +271,13 @@ def cg_update(P, AP, X, R, rs_old, pAp, eps: float, rs_new):
     _req(P, torch.float32, "P")
     _check(load().sa_cg_update(_stream(), P.shape[0], P.shape[1], P.data_ptr(), _ptr(AP), X.data_ptr(),
                                _ptr(R), rs_old.data_ptr(), pAp.data_ptr(), float(eps), _ptr(rs_new)))
+    STATS.launches += 1
 
 
 def cg_direction(R, P, rs_new, rs_old):
     _check(load().sa_cg_direction(_stream(), P.shape[0], P.shape[1], R.data_ptr(), P.data_ptr(),
                                   rs_new.data_ptr(), rs_old.data_ptr()))
+    STATS.launches += 1
 
 
 def axpby(a: float, X: torch.Tensor, b: float, Y: torch.Tensor):
@@ -230,6 +286,7 @@ def axpby(a: float, X: torch.Tensor, b: float, Y: torch.Tensor):
     if X.numel() != Y.numel():
         raise ValueError("size mismatch")
     _check(load().sa_axpby(_stream(), X.numel(), float(a), X.data_ptr(), float(b), Y.data_ptr()))
+    STATS.launches += 1
     return Y
 
 

@@ -12,7 +12,9 @@
 //               work unit ends.  K(A, B) only ever exists in TMEM and registers.
 //
 // Work decomposition: units = row tiles x nsplit column chunks, round-robin over the CTAs with the
-// row tile varying fastest so concurrently running CTAs sweep the same B tiles (L2 reuse).
+// chunk index varying fastest: the CTAs running at the same time then cover only sms/nsplit row
+// tiles, so their A strips (128 x p fp16 each, re-read once per column tile) stay L2 resident while
+// CTAs on the same chunk sweep the same B tiles in step.
 //
 // Replaces falkon `Kernel.mmv / dmmv / __call__` [external dependency of the reference], reached
 // from /root/reference/sobolev_alignment/krr_approx.py:227,314 and sobolev_alignment.py:950,955-958.
@@ -42,6 +44,17 @@ constexpr int MAX_STAGES = 4;
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_BARS = 16;
 constexpr float LOG2E = 1.4426950408889634f;
+// The tcgen05 fp32 accumulator is not round-to-nearest: every K=16 MMA step truncates ~2^-22.4 of the
+// running sum.  For rows that coincide (every Nystrom centre is also a training row) the products
+// are all positive, the dot product comes out low by ACC_BIAS_PER_STEP * steps (measured on B200 with
+// tools/gpu_check.py accum: 0.63e-7 .. 0.85e-7 per step for 32..256 steps, +-15 % between rows), and
+// sqrt() turns that into a visible error of k(x, x).  The epilogue therefore (1) rescales the dot
+// product by the calibrated gain -- exact to first order for coincident / nearly coincident rows, a
+// no-op for the typical pair whose centred dot product is ~0 -- and (2) snaps what is left below the
+// residual resolution to exactly zero, so that k(x, x) = 1.
+constexpr float ACC_BIAS_PER_STEP = 0.8e-7f;
+constexpr float SNAP_PER_STEP = 0.3e-7f;
+constexpr float SNAP_FLOOR = 4.0e-7f;
 
 struct Params {
   long long a, b;   // rows of A / rows of B
@@ -56,6 +69,8 @@ struct Params {
   float* out;
   long long ldo;
   float c0;         // gaussian: kscale*log2e ; others: kscale * sqrt(nu factor)
+  float snap;       // squared distances below snap * (|a|^2 + |b|^2) are treated as exactly zero
+  float m2g;        // -2 * (1 + accumulator-bias compensation)
   int symmetric;
 };
 
@@ -126,8 +141,8 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       int s = 0;
       uint32_t ph = 0;
       for (int unit = blockIdx.x; unit < P.units; unit += gridDim.x) {
-        const int rt = unit % P.ta;
-        const int ch = unit / P.ta;
+        const int rt = unit / P.nsplit;
+        const int ch = unit % P.nsplit;
         const int j0 = static_cast<int>(static_cast<long long>(ch) * P.tb / P.nsplit);
         const int j1 = static_cast<int>(static_cast<long long>(ch + 1) * P.tb / P.nsplit);
         for (int j = j0; j < j1; ++j) {
@@ -152,7 +167,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       int buf = 0;
       uint32_t tph = 0;
       for (int unit = blockIdx.x; unit < P.units; unit += gridDim.x) {
-        const int ch = unit / P.ta;
+        const int ch = unit % P.nsplit;
         const int j0 = static_cast<int>(static_cast<long long>(ch) * P.tb / P.nsplit);
         const int j1 = static_cast<int>(static_cast<long long>(ch + 1) * P.tb / P.nsplit);
         for (int j = j0; j < j1; ++j) {
@@ -186,7 +201,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       int vb = 0;
       uint32_t vph = 0;
       for (int unit = blockIdx.x; unit < P.units; unit += gridDim.x) {
-        const int ch = unit / P.ta;
+        const int ch = unit % P.nsplit;
         const int j0 = static_cast<int>(static_cast<long long>(ch) * P.tb / P.nsplit);
         const int j1 = static_cast<int>(static_cast<long long>(ch + 1) * P.tb / P.nsplit);
         for (int j = j0; j < j1; ++j) {
@@ -216,8 +231,8 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     int vb = 0;
     uint32_t vph = 0;
     for (int unit = blockIdx.x; unit < P.units; unit += gridDim.x) {
-      const int rt = unit % P.ta;
-      const int ch = unit / P.ta;
+      const int rt = unit / P.nsplit;
+      const int ch = unit % P.nsplit;
       const int j0 = static_cast<int>(static_cast<long long>(ch) * P.tb / P.nsplit);
       const int j1 = static_cast<int>(static_cast<long long>(ch + 1) * P.tb / P.nsplit);
       const long long grow = static_cast<long long>(rt) * BM + row_in_tile;
@@ -248,8 +263,9 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             float kv[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-              float d2 = fmaxf(fmaf(-2.f, __uint_as_float(r[c]), na + Ns[c0 + c]), 0.f);
-              if (col0 + c0 + c == sym_row) d2 = 0.f;
+              const float nn = na + Ns[c0 + c];
+              float d2 = fmaf(P.m2g, __uint_as_float(r[c]), nn);
+              if (d2 < P.snap * nn || col0 + c0 + c == sym_row) d2 = 0.f;
               kv[c] = kernel_value<KID>(d2, P.c0);
             }
             if (row_ok) {
@@ -269,8 +285,9 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               if (full_chunk || (c0 + c < cend)) {
-                float d2 = fmaxf(fmaf(-2.f, __uint_as_float(r[c]), na + Ns[c0 + c]), 0.f);
-                if (col0 + c0 + c == sym_row) d2 = 0.f;
+                const float nn = na + Ns[c0 + c];
+                float d2 = fmaf(P.m2g, __uint_as_float(r[c]), nn);
+                if (d2 < P.snap * nn || col0 + c0 + c == sym_row) d2 = 0.f;
                 const float kv = kernel_value<KID>(d2, P.c0);
                 const float4* vrow = reinterpret_cast<const float4*>(Vs + (c0 + c) * DP);
 #pragma unroll
@@ -378,14 +395,21 @@ static int env_int(const char* name, int dflt) {
   return v ? std::atoi(v) : dflt;
 }
 
-// cost model: waves x (column tiles per unit + fixed per-unit overhead)
-static int choose_nsplit(int ta, int tb, int sms) {
+// cost model: waves x (column tiles per unit + fixed per-unit overhead), subject to the A strips of
+// the concurrently running row tiles fitting an L2 budget
+static int choose_nsplit(int ta, int tb, int sms, long long p_pad) {
   int forced = env_int("SAB_NSPLIT", 0);
   if (forced > 0) return forced < tb ? forced : tb;
+  const double l2_budget = static_cast<double>(env_int("SAB_L2_BUDGET_MB", 32)) * 1048576.0;
+  const double strip = static_cast<double>(BM) * static_cast<double>(p_pad) * 2.0;
+  const int live = ta < sms ? ta : sms;
+  int min_ns = static_cast<int>(live * strip / l2_budget) + 1;
+  if (min_ns > tb) min_ns = tb;
+  if (min_ns < 1) min_ns = 1;
   double best = 1e300;
-  int best_ns = 1;
+  int best_ns = min_ns;
   const int max_ns = tb < 1024 ? tb : 1024;
-  for (int ns = 1; ns <= max_ns; ++ns) {
+  for (int ns = min_ns; ns <= max_ns; ++ns) {
     const double waves = static_cast<double>(ceil_div(static_cast<int64_t>(ta) * ns, sms));
     const double len = static_cast<double>(ceil_div(tb, ns)) + 0.35;
     const double cost = waves * len;
@@ -456,7 +480,7 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   P.kblocks = static_cast<int>(p_pad / BK);
   P.ta = static_cast<int>(ceil_div(a, BM));
   P.tb = static_cast<int>(ceil_div(b, BN));
-  P.nsplit = dense ? 1 : choose_nsplit(P.ta, P.tb, di.sms);
+  P.nsplit = dense ? 1 : choose_nsplit(P.ta, P.tb, di.sms, p_pad);
   P.units = P.ta * P.nsplit;
   P.nA = nA;
   P.nB = nB;
@@ -464,6 +488,13 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   P.out = out;
   P.ldo = ldo;
   P.symmetric = symmetric;
+  {
+    const float steps = static_cast<float>(P.kblocks * (BK / UMMA_K));
+    const char* sv = std::getenv("SAB_SNAP");   // < 0 disables both corrections (calibration runs)
+    const float forced = sv ? static_cast<float>(std::atof(sv)) : 0.f;
+    P.snap = sv ? forced : SNAP_PER_STEP * steps + SNAP_FLOOR;
+    P.m2g = (sv && forced < 0.f) ? -2.f : -2.f * (1.f + ACC_BIAS_PER_STEP * steps);
+  }
   if (kernel == SA_KERNEL_GAUSSIAN) P.c0 = kscale * LOG2E;
   else if (kernel == SA_KERNEL_LAPLACIAN) P.c0 = kscale;
   else if (kernel == SA_KERNEL_MATERN15) P.c0 = kscale * 1.7320508075688772f;

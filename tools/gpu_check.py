@@ -197,9 +197,35 @@ def bench_linalg():
               f"bwd {t4*1e3:.2f} ms info={int(info)}")
 
 
+
+
+def check_accum():
+    """How far is |a|^2+|a|^2-2a.a from zero (relative to |a|^2+|a|^2)?  tcgen05 accumulation resolution."""
+    import numpy as np
+    os.environ["SAB_SNAP"] = "-1"   # disable the snap: look at the raw computed distances
+    from sobolev_alignment_b200 import synthetic as syn
+    for p in (64, 256, 512, 1024, 2048, 3000, 4096):
+        for name, A in (("normal", torch.randn(1024, p, device=dev)),
+                        ("positive", torch.rand(1024, p, device=dev) + 0.5),
+                        ("logcounts_centred", None)):
+            if A is None:
+                Xn = torch.from_numpy(syn.log_counts_numpy(1024, p, seed=p)).to(dev)
+                A = (Xn - Xn.mean(0)) * 8.0
+            PA = nat.prep(A.contiguous(), None, None, 1.0)
+            out = torch.empty(1024, 1024, device=dev)
+            # gaussian with kscale 1: K = exp(-d2)  =>  d2 = -log K on the diagonal
+            nat.kdense(0, 1.0, PA, PA, out)
+            torch.cuda.synchronize()
+            d2 = -torch.log(out.diagonal().double())
+            nn = 2 * PA.norms[:1024].double()
+            ratio = (d2 / nn)
+            print(f"accum p={p:5d} {name:18s}: d2/nn  max={float(ratio.max()):.3e} mean={float(ratio.mean()):.3e} "
+                  f"min={float(ratio.min()):.3e}  per-MMA-step={float(ratio.max()) / (nat.round_up(p, 64) / 16):.3e}")
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     t0 = time.time()
     {"prep": check_prep, "kdense": check_kdense, "kmv": check_kmv, "linalg": check_linalg,
-     "bench_kmv": bench_kmv, "bench_linalg": bench_linalg}[what]()
+     "bench_kmv": bench_kmv, "bench_linalg": bench_linalg, "accum": check_accum}[what]()
     print(f"[{what}] done in {time.time() - t0:.1f}s")
