@@ -61,13 +61,18 @@ int sa_prep(void* stream, const float* X, int64_t n, int64_t p, int64_t ldx, con
  * Fused kernel-matrix x matrix product, K never materialised (falkon `Kernel.mmv` and each half of
  * `Kernel.dmmv` [ext]; reached from `Falkon.fit` krr_approx.py:227 and `Falkon.predict` :314):
  *   out[a x dp] += k(A, B) @ V[b x dp]
- * A [a x p_pad], B [b x p_pad] are prepared operands with norms nA, nB.  `out` is accumulated into
- * with atomic adds (the caller zeroes it for a plain product).  `symmetric` != 0 asserts A == B
- * so the exact zero distance is used on the diagonal.
+ * A [a x p_pad], B [b x p_pad] are prepared operands with norms nA, nB.  V and out are fp32,
+ * row-major, dense (row stride dp).  `out` is accumulated into with atomic adds (the caller zeroes
+ * it for a plain product).  `symmetric` != 0 asserts A == B so the exact zero distance is used on
+ * the diagonal.  `workspace` is caller-owned scratch of at least sa_kmv_workspace_bytes(b, dp)
+ * bytes, 128-byte aligned: the library writes the per-column scales of V and its fp16 hi/lo tiles
+ * there before the main kernel (same stream); it may be reused by the next call on that stream.
  */
+int64_t sa_kmv_workspace_bytes(int64_t b, int dp);
 int sa_kmv(void* stream, int kernel, float kscale, const void* A, const float* nA, int64_t a,
            int64_t lda, const void* B, const float* nB, int64_t b, int64_t ldb, int64_t p_pad,
-           const float* V, int dp, float* out, int symmetric);
+           const float* V, int dp, float* out, int symmetric, void* workspace,
+           int64_t workspace_bytes);
 
 /*
  * Dense kernel matrix (falkon `Kernel.__call__` [ext]; called as `kernel_(A, B)` at

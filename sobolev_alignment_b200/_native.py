@@ -66,8 +66,9 @@ _SIGNATURES = {
     "sa_device_info": (c_int, [c_void_p, c_void_p]),
     "sa_prep": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_float,
                         c_void_p, c_int64, c_void_p, c_int64]),
+    "sa_kmv_workspace_bytes": (c_int64, [c_int64, c_int]),
     "sa_kmv": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
-                       c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int]),
+                       c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64]),
     "sa_kdense": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                           c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int]),
     "sa_potrf": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
@@ -177,8 +178,21 @@ def alloc_prepared(n: int, p: int, device) -> Prepared:
     return Prepared(data, norms, n, p)
 
 
+_workspaces = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    """Scratch for the V pre-pass of sa_kmv, one growing buffer per device (stream-ordered reuse)."""
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
 def kmv(kernel_id: int, kscale: float, A: Prepared, B: Prepared, V: torch.Tensor, out: torch.Tensor,
-        symmetric: bool = False, a_rows: slice | None = None):
+        symmetric: bool = False):
     """out[a x dp] += k(A, B) @ V[b x dp]   (out must be zeroed by the caller for a plain product)."""
     lib = load()
     _req(V, torch.float32, "V")
@@ -192,14 +206,18 @@ def kmv(kernel_id: int, kscale: float, A: Prepared, B: Prepared, V: torch.Tensor
     if STATS.time_kmv:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
+    nbytes = int(lib.sa_kmv_workspace_bytes(B.n, dp))
+    if nbytes < 0:
+        raise NativeLibraryError(f"dp must be a multiple of 4 in [4, 32], got {dp}")
+    ws = _workspace(V.device, nbytes)
     _check(lib.sa_kmv(_stream(), kernel_id, float(kscale), A.data.data_ptr(), A.norms.data_ptr(), A.n,
                       A.p_pad, B.data.data_ptr(), B.norms.data_ptr(), B.n, B.p_pad, A.p_pad,
-                      V.data_ptr(), dp, out.data_ptr(), int(symmetric)))
+                      V.data_ptr(), dp, out.data_ptr(), int(symmetric), ws.data_ptr(), ws.numel()))
     if ev is not None:
         ev[1].record()
         # algorithmic work: 2 a b p + 2 a b d, with the caller's p and padded d
         STATS.kmv_events.append((2.0 * A.n * B.n * (A.p + dp), ev[0], ev[1]))
-    STATS.launches += 1
+    STATS.launches += 3   # column maxima, fp16 split of V, fused kernel
     return out
 
 

@@ -1,15 +1,24 @@
 // Fused kernel-matrix x matrix product for sm_100a:   out[a x dp] += k(A, B) @ V      (sa_kmv)
 // and the dense variant                               out[a x b]   = k(A, B)          (sa_kdense)
 //
-// One persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer: 128x64 tile of A and 256x64 tile of B (fp16, 128B swizzle) per stage
-//   warp 1      MMA issuer: tcgen05.mma kind::f16, M=128 N=256 K=16, fp32 accumulator in TMEM
-//               (two 256-column accumulators = all 512 TMEM columns, double buffered)
-//   warp 2      TMEM allocator + bulk loader of the V tile [256 x dp] and the B-norm tile
-//   warps 4-11  epilogue: tcgen05.ld the dot products, d2 = |a|^2 + |b|^2 - 2 a.b, kernel function
-//               (sqrt / exp2 on the SFU), then the thin product with V on the FMA pipe; each thread
-//               owns one row of the tile and dp running sums, flushed with red.global.add when the
-//               work unit ends.  K(A, B) only ever exists in TMEM and registers.
+// One persistent CTA per SM, warp-specialised, two chained tensor-core products per tile (the
+// structure of a Blackwell attention kernel with the softmax replaced by the kernel function):
+//
+//   warp 0      TMA producer: 128x64 tile of A and 224x64 tile of B (fp16, 128B swizzle) per stage
+//   warp 1      MMA issuer.  (1) S = A B^T: tcgen05.mma kind::f16 SS, M=128 N=224 K=16, fp32 in TMEM
+//               columns [0,224) / [224,448) (double buffered).  (2) O += P V: tcgen05.mma TS with the
+//               A operand P read straight from TMEM (where the epilogue wrote it over S) and the V
+//               tile from shared memory, accumulators O1/O2 in TMEM columns [448,480) / [480,512).
+//   warp 2      TMEM allocator + bulk loader of the fp16 V tile and the B-norm tile
+//   warps 4-11  epilogue: tcgen05.ld 16 columns of S, d2 = |a|^2 + |b|^2 - 2 a.b, kernel function
+//               (sqrt / exp2 on the SFU), split k into fp16 hi + scaled fp16 lo, tcgen05.st both
+//               back over the S columns just read.  O is read out once per work unit and added to
+//               the output with red.global.add.
+//
+// K(A, B) only ever exists in TMEM and registers.  P and V are carried as hi + 2^-11 lo fp16 pairs
+// (three small MMAs per 16 columns: hi*hi -> O1, lo*hi + hi*lo -> O2), so the thin product keeps
+// ~22 bits although it runs on the fp16 tensor path; V is pre-scaled per column to the top of the
+// fp16 range by a tiny pre-pass (sa_kmv workspace).
 //
 // Work decomposition: units = row tiles x nsplit column chunks, round-robin over the CTAs with the
 // chunk index varying fastest: the CTAs running at the same time then cover only sms/nsplit row
@@ -19,6 +28,7 @@
 // Replaces falkon `Kernel.mmv / dmmv / __call__` [external dependency of the reference], reached
 // from /root/reference/sobolev_alignment/krr_approx.py:227,314 and sobolev_alignment.py:950,955-958.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 #include <mutex>
@@ -31,19 +41,27 @@ namespace sab {
 namespace kmv {
 
 constexpr int BM = 128;
-constexpr int BN = 256;
+constexpr int BN = 224;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int A_BYTES = BM * BK * 2;
-constexpr int B_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int A_BYTES = BM * BK * 2;            // 16384
+constexpr int B_BYTES = BN * BK * 2;            // 28672
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 45056 (multiple of 1024)
 constexpr int FIRST_EPI_WARP = 4;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;
 constexpr int MAX_STAGES = 4;
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_BARS = 16;
+constexpr int TM_S0 = 0, TM_S1 = BN, TM_O1 = 2 * BN, TM_O2 = 2 * BN + 32;
+constexpr int PV_STEPS = BN / UMMA_K;  // 14
+constexpr int HALF_COLS = BN / 2;      // 112 columns per epilogue warp
+constexpr int NB_FLOATS = 256;         // shared-memory slot of the B-norm tile
+constexpr int NUM_BARS = 18;
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr float K_SCALE_LOG2 = 14.f;   // k values are carried as k * 2^14 in fp16
+constexpr float LO_GAIN = 2048.f;      // the fp16 residual is carried as (x - hi) * 2^11
+constexpr int WS_HEADER_BYTES = 256;   // per-column max |V| (32 floats) + padding
+
 // The tcgen05 fp32 accumulator is not round-to-nearest: every K=16 MMA step truncates ~2^-22.4 of the
 // running sum.  For rows that coincide (every Nystrom centre is also a training row) the products
 // are all positive, the dot product comes out low by ACC_BIAS_PER_STEP * steps (measured on B200 with
@@ -56,80 +74,135 @@ constexpr float ACC_BIAS_PER_STEP = 0.8e-7f;
 constexpr float SNAP_PER_STEP = 0.3e-7f;
 constexpr float SNAP_FLOOR = 4.0e-7f;
 
+__host__ __device__ constexpr int pv_n(int dp) { return dp <= 16 ? 16 : 32; }
+// bytes of one V tile in the workspace / in shared memory: hi block + lo block
+__host__ __device__ constexpr int vtile_bytes(int dp) { return 2 * PV_STEPS * pv_n(dp) * UMMA_K * 2; }
+
 struct Params {
-  long long a, b;   // rows of A / rows of B
-  int kblocks;      // p_pad / 64
-  int ta, tb;       // row tiles, column tiles
-  int nsplit;       // column chunks per row tile
-  int units;        // ta * nsplit
+  long long a, b;  // rows of A / rows of B
+  int kblocks;     // p_pad / 64
+  int ta, tb;      // row tiles, column tiles
+  int nsplit;      // column chunks per row tile
+  int units;       // ta * nsplit
   int stages, vbufs;
   const float* nA;
   const float* nB;
-  const float* V;
+  const uint8_t* vws;  // workspace: header (column maxima) + fp16 V tiles
   float* out;
   long long ldo;
-  float c0;         // gaussian: kscale*log2e ; others: kscale * sqrt(nu factor)
-  float snap;       // squared distances below snap * (|a|^2 + |b|^2) are treated as exactly zero
-  float m2g;        // -2 * (1 + accumulator-bias compensation)
+  float c0;    // gaussian: kscale*log2e ; others: kscale * sqrt(nu factor)
+  float snap;  // squared distances below snap * (|a|^2 + |b|^2) are treated as exactly zero
+  float m2g;   // -2 * (1 + accumulator-bias compensation)
   int symmetric;
 };
 
+// k(d2) * 2^shift  (shift = 14 for the fused product so that k fills the fp16 range, 0 for dense)
 template <int KID>
-__device__ __forceinline__ float kernel_value(float d2, float c0) {
+__device__ __forceinline__ float kernel_value(float d2, float c0, float shift) {
   if (KID == SA_KERNEL_GAUSSIAN) {
-    return ex2_approx(-c0 * d2);
+    return ex2_approx(fmaf(-c0, d2, shift));
   } else {
     const float s = c0 * sqrt_approx(d2);  // laplacian: r ; matern: sqrt(2 nu) r
-    const float e = ex2_approx(-LOG2E * s);
+    const float e = ex2_approx(fmaf(-LOG2E, s, shift));
     if (KID == SA_KERNEL_LAPLACIAN) return e;
     if (KID == SA_KERNEL_MATERN15) return fmaf(s, e, e);
     return fmaf(fmaf(s, 0.33333333333f, 1.0f), s, 1.0f) * e;
   }
 }
 
+// scale that brings a column whose largest magnitude has the float bits `maxbits` into [2^13, 2^14)
+__device__ __forceinline__ void column_scale(uint32_t maxbits, float* scale, float* inv) {
+  int e = static_cast<int>((maxbits >> 23) & 0xffu) - 127;
+  if (maxbits == 0u || e > 100 || e < -100) e = 13;  // empty / degenerate column: scale 1
+  *scale = __uint_as_float(static_cast<uint32_t>(13 - e + 127) << 23);
+  *inv = __uint_as_float(static_cast<uint32_t>(e - 13 + 127) << 23);
+}
+
+// iterates the (unit, column tile) pairs this CTA owns, in execution order
+struct TileIter {
+  int unit, j, j0, j1;
+  __device__ __forceinline__ void set_range(const Params& P) {
+    const int ch = unit % P.nsplit;
+    j0 = static_cast<int>(static_cast<long long>(ch) * P.tb / P.nsplit);
+    j1 = static_cast<int>(static_cast<long long>(ch + 1) * P.tb / P.nsplit);
+    j = j0;
+  }
+  __device__ __forceinline__ explicit TileIter(const Params& P)
+      : unit(static_cast<int>(blockIdx.x)), j(0), j0(0), j1(0) {
+    if (unit < P.units) set_range(P);
+  }
+  __device__ __forceinline__ bool valid(const Params& P) const { return unit < P.units; }
+  __device__ __forceinline__ bool first() const { return j == j0; }
+  __device__ __forceinline__ bool last() const { return j + 1 == j1; }
+  __device__ __forceinline__ int row_tile(const Params& P) const { return unit / P.nsplit; }
+  __device__ __forceinline__ void next(const Params& P) {
+    if (++j == j1) {
+      unit += static_cast<int>(gridDim.x);
+      if (unit < P.units) set_range(P);
+    }
+  }
+};
+
 template <int KID, int DP, bool DENSE>
 __global__ void __launch_bounds__(THREADS, 1)
 kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
            const Params P) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  constexpr int VBUF_FLOATS = DENSE ? 0 : BN * DP;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NP = pv_n(DP);
+  constexpr int VT_BYTES = DENSE ? 0 : vtile_bytes(DP);
+  constexpr int VLO_OFF = VT_BYTES / 2;
   uint8_t* tiles = smem;
-  float* vbuf = reinterpret_cast<float*>(tiles + P.stages * STAGE_BYTES);
-  float* nbuf = vbuf + P.vbufs * VBUF_FLOATS;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(nbuf + P.vbufs * BN);
+  uint8_t* vbuf = tiles + P.stages * STAGE_BYTES;
+  float* nbuf = reinterpret_cast<float*>(vbuf + P.vbufs * VT_BYTES);
+  float* vinv = nbuf + P.vbufs * NB_FLOATS;  // [32] 2^-14 / column scale
+  uint64_t* bars = reinterpret_cast<uint64_t*>(vinv + 32);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
 
-  const uint32_t bar_full = smem_u32(bars + 0);     // [MAX_STAGES] TMA -> MMA
-  const uint32_t bar_empty = smem_u32(bars + 4);    // [MAX_STAGES] MMA -> TMA
-  const uint32_t bar_tfull = smem_u32(bars + 8);    // [2] MMA -> epilogue (accumulator ready)
-  const uint32_t bar_tempty = smem_u32(bars + 10);  // [2] epilogue -> MMA (accumulator drained)
+  const uint32_t bar_full = smem_u32(bars + 0);     // [4] TMA -> MMA
+  const uint32_t bar_empty = smem_u32(bars + 4);    // [4] MMA -> TMA
+  const uint32_t bar_sfull = smem_u32(bars + 8);    // [2] S accumulator ready -> epilogue
+  const uint32_t bar_pready = smem_u32(bars + 10);  // [2] epilogue wrote P (dense: drained S) -> MMA
   const uint32_t bar_vfull = smem_u32(bars + 12);   // [2] V / norm tile landed
   const uint32_t bar_vempty = smem_u32(bars + 14);  // [2] V / norm tile consumed
+  const uint32_t bar_ofull = smem_u32(bars + 16);   // O accumulators of a unit complete
+  const uint32_t bar_oempty = smem_u32(bars + 17);  // O accumulators read out
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("sobolev_b200: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, EPI_WARPS);
+      mbar_init(bar_sfull + 8 * i, 1);
+      mbar_init(bar_pready + 8 * i, EPI_WARPS);
       mbar_init(bar_vfull + 8 * i, 1);
-      mbar_init(bar_vempty + 8 * i, EPI_WARPS);
+      mbar_init(bar_vempty + 8 * i, DENSE ? EPI_WARPS : EPI_WARPS + 1);
     }
+    mbar_init(bar_ofull, 1);
+    mbar_init(bar_oempty, EPI_WARPS / 2);
     fence_barrier_init();
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
+  }
+  // norm slots must hold finite values before the first (possibly ragged) tile lands
+  for (int i = threadIdx.x; i < P.vbufs * NB_FLOATS; i += THREADS) nbuf[i] = 0.f;
+  if (!DENSE && threadIdx.x < 32) {
+    float sc, inv;
+    column_scale(reinterpret_cast<const uint32_t*>(P.vws)[threadIdx.x], &sc, &inv);
+    vinv[threadIdx.x] = inv * 6.103515625e-05f;  // 2^-14: undo the scaling of k as well
   }
   if (warp == 2) {
     tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     tmem_relinquish();
   }
+  fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -140,58 +213,94 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int unit = blockIdx.x; unit < P.units; unit += gridDim.x) {
-        const int rt = unit / P.nsplit;
-        const int ch = unit % P.nsplit;
-        const int j0 = static_cast<int>(static_cast<long long>(ch) * P.tb / P.nsplit);
-        const int j1 = static_cast<int>(static_cast<long long>(ch + 1) * P.tb / P.nsplit);
-        for (int j = j0; j < j1; ++j) {
-          for (int kb = 0; kb < P.kblocks; ++kb) {
-            mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            const uint32_t full = bar_full + 8 * s;
-            mbar_arrive_expect_tx(full, STAGE_BYTES);
-            const uint32_t dstA = smem_u32(tiles + s * STAGE_BYTES);
-            tma_load_2d(dstA, &tmA, full, kb * BK, rt * BM);
-            tma_load_2d(dstA + A_BYTES, &tmB, full, kb * BK, j * BN);
-            if (++s == P.stages) { s = 0; ph ^= 1; }
-          }
+      for (TileIter it(P); it.valid(P); it.next(P)) {
+        const int rt = it.row_tile(P);
+        for (int kb = 0; kb < P.kblocks; ++kb) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t full = bar_full + 8 * s;
+          mbar_arrive_expect_tx(full, STAGE_BYTES);
+          const uint32_t dstA = smem_u32(tiles + s * STAGE_BYTES);
+          tma_load_2d(dstA, &tmA, full, kb * BK, rt * BM);
+          tma_load_2d(dstA + A_BYTES, &tmB, full, kb * BK, it.j * BN);
+          if (++s == P.stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+      constexpr uint32_t idesc_s = umma_idesc_f16(BM, BN);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(BM, NP);
       int s = 0;
       uint32_t ph = 0;
-      int buf = 0;
-      uint32_t tph = 0;
-      for (int unit = blockIdx.x; unit < P.units; unit += gridDim.x) {
-        const int ch = unit % P.nsplit;
-        const int j0 = static_cast<int>(static_cast<long long>(ch) * P.tb / P.nsplit);
-        const int j1 = static_cast<int>(static_cast<long long>(ch + 1) * P.tb / P.nsplit);
-        for (int j = j0; j < j1; ++j) {
-          mbar_wait(bar_tempty + 8 * buf, ((tph >> buf) & 1u) ^ 1u);
+      // S = A B^T for one column tile into accumulator `buf`
+      auto issue_s = [&](int buf) {
+        const uint32_t tacc = tmem_base + static_cast<uint32_t>(buf ? TM_S1 : TM_S0);
+        for (int kb = 0; kb < P.kblocks; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph);
           tcgen05_fence_after();
-          const uint32_t tacc = tmem_base + static_cast<uint32_t>(buf * BN);
-          for (int kb = 0; kb < P.kblocks; ++kb) {
-            mbar_wait(bar_full + 8 * s, ph);
-            tcgen05_fence_after();
-            const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES);
-            const uint64_t da = umma_smem_desc_sw128(sa);
-            const uint64_t db = umma_smem_desc_sw128(sa + A_BYTES);
+          const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES);
+          const uint64_t da = umma_smem_desc_sw128(sa);
+          const uint64_t db = umma_smem_desc_sw128(sa + A_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              // advance 16 fp16 = 32 B along K inside the 128 B swizzle atom: +2 in 16-byte units
-              umma_f16_ss(tacc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                          idesc, (kb | k) != 0 ? 1u : 0u);
-            }
-            umma_commit(bar_empty + 8 * s);  // stage reusable once these MMAs retire
-            if (kb == P.kblocks - 1) umma_commit(bar_tfull + 8 * buf);
-            if (++s == P.stages) { s = 0; ph ^= 1; }
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 fp16 = 32 B along K inside the 128 B swizzle atom: +2 in 16-byte units
+            umma_f16_ss(tacc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                        idesc_s, (kb | k) != 0 ? 1u : 0u);
           }
-          tph ^= (1u << buf);
-          buf ^= 1;
+          umma_commit(bar_empty + 8 * s);  // stage reusable once these MMAs retire
+          if (kb == P.kblocks - 1) umma_commit(bar_sfull + 8 * buf);
+          if (++s == P.stages) { s = 0; ph ^= 1; }
+        }
+      };
+
+      if (DENSE) {
+        uint32_t t = 0;
+        for (TileIter it(P); it.valid(P); it.next(P), ++t) {
+          const int buf = t & 1;
+          mbar_wait(bar_pready + 8 * buf, ((t >> 1) & 1u) ^ 1u);  // epilogue drained this buffer
+          tcgen05_fence_after();
+          issue_s(buf);
+        }
+      } else {
+        TileIter ahead(P), cur(P);
+        // the S product runs two tiles ahead of the P V product
+        if (ahead.valid(P)) { issue_s(0); ahead.next(P); }
+        if (ahead.valid(P)) { issue_s(1); ahead.next(P); }
+        uint32_t t = 0, ophase = 0;
+        int vb = 0;
+        uint32_t vph = 0;
+        for (; cur.valid(P); cur.next(P), ++t) {
+          const int buf = t & 1;
+          mbar_wait(bar_pready + 8 * buf, (t >> 1) & 1u);  // P(t) is in TMEM
+          mbar_wait(bar_vfull + 8 * vb, vph);              // V(t) is in shared memory
+          if (cur.first() && t != 0) {                     // previous unit's O has been read out
+            mbar_wait(bar_oempty, ophase);
+            ophase ^= 1;
+          }
+          tcgen05_fence_after();
+          const uint32_t tp = tmem_base + static_cast<uint32_t>(buf ? TM_S1 : TM_S0);
+          const uint32_t vs = smem_u32(vbuf + vb * VT_BYTES);
+#pragma unroll
+          for (int st = 0; st < PV_STEPS; ++st) {
+            // V tile: per 16-column step NP x 16 fp16, 8x8 core matrices, K-major, no swizzle:
+            // core (n/8, k/8) at ((n/8)*2 + k/8) * 128 B  ->  LBO (K) = 128 B, SBO (N) = 256 B
+            const uint64_t dhi = umma_smem_desc_noswz(vs + st * (NP * 32), 128, 256);
+            const uint64_t dlo = umma_smem_desc_noswz(vs + VLO_OFF + st * (NP * 32), 128, 256);
+            const uint32_t phi = tp + static_cast<uint32_t>(16 * st);  // 8 columns = 16 fp16 of hi
+            const uint32_t plo = phi + 8;                               // then 8 columns of lo
+            const uint32_t acc = (cur.first() && st == 0) ? 0u : 1u;
+            umma_f16_ts(tmem_base + TM_O1, phi, dhi, idesc_pv, acc);
+            umma_f16_ts(tmem_base + TM_O2, plo, dhi, idesc_pv, acc);
+            umma_f16_ts(tmem_base + TM_O2, phi, dlo, idesc_pv, 1u);
+          }
+          umma_commit(bar_vempty + 8 * vb);
+          if (cur.last()) umma_commit(bar_ofull);
+          if (ahead.valid(P)) {  // S(t+2) reuses the TMEM columns of P(t): in issue order behind P V(t)
+            issue_s(buf);
+            ahead.next(P);
+          }
+          if (++vb == P.vbufs) { vb = 0; vph ^= 1; }
         }
       }
     }
@@ -200,123 +309,124 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     if (lane == 0) {
       int vb = 0;
       uint32_t vph = 0;
-      for (int unit = blockIdx.x; unit < P.units; unit += gridDim.x) {
-        const int ch = unit % P.nsplit;
-        const int j0 = static_cast<int>(static_cast<long long>(ch) * P.tb / P.nsplit);
-        const int j1 = static_cast<int>(static_cast<long long>(ch + 1) * P.tb / P.nsplit);
-        for (int j = j0; j < j1; ++j) {
-          mbar_wait(bar_vempty + 8 * vb, vph ^ 1);
-          const long long col0 = static_cast<long long>(j) * BN;
-          const int cols_valid = static_cast<int>(min(static_cast<long long>(BN), P.b - col0));
-          const uint32_t full = bar_vfull + 8 * vb;
-          const uint32_t vbytes = DENSE ? 0u : static_cast<uint32_t>(cols_valid * DP * 4);
-          mbar_arrive_expect_tx(full, BN * 4 + vbytes);
-          bulk_load_1d(smem_u32(nbuf + vb * BN), P.nB + col0, BN * 4, full);
-          if (!DENSE)
-            bulk_load_1d(smem_u32(vbuf + vb * VBUF_FLOATS), P.V + col0 * DP, vbytes, full);
-          if (++vb == P.vbufs) { vb = 0; vph ^= 1; }
-        }
+      for (TileIter it(P); it.valid(P); it.next(P)) {
+        mbar_wait(bar_vempty + 8 * vb, vph ^ 1);
+        const long long col0 = static_cast<long long>(it.j) * BN;
+        const int cols_valid = static_cast<int>(min(static_cast<long long>(BN), P.b - col0));
+        const uint32_t nbytes = static_cast<uint32_t>((cols_valid + 3) & ~3) * 4u;
+        const uint32_t full = bar_vfull + 8 * vb;
+        mbar_arrive_expect_tx(full, nbytes + VT_BYTES);
+        bulk_load_1d(smem_u32(nbuf + vb * NB_FLOATS), P.nB + col0, nbytes, full);
+        if (!DENSE)
+          bulk_load_1d(smem_u32(vbuf + vb * VT_BYTES),
+                       P.vws + WS_HEADER_BYTES + static_cast<long long>(it.j) * VT_BYTES, VT_BYTES, full);
+        if (++vb == P.vbufs) { vb = 0; vph ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp >= FIRST_EPI_WARP) {
     // ======================================= epilogue =======================================
     const int e = warp - FIRST_EPI_WARP;
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
-    const int half = e >> 2;       // which 128 columns of the 256-wide accumulator
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = e >> 2;       // which 112 columns of the 224-wide accumulator
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t tlane = static_cast<uint32_t>(quarter * 32) << 16;
-    int buf = 0;
-    uint32_t tph = 0;
+    const int cbeg = half * HALF_COLS;
+    uint32_t t = 0, ophase = 0;
     int vb = 0;
     uint32_t vph = 0;
-    for (int unit = blockIdx.x; unit < P.units; unit += gridDim.x) {
-      const int rt = unit / P.nsplit;
-      const int ch = unit % P.nsplit;
-      const int j0 = static_cast<int>(static_cast<long long>(ch) * P.tb / P.nsplit);
-      const int j1 = static_cast<int>(static_cast<long long>(ch + 1) * P.tb / P.nsplit);
-      const long long grow = static_cast<long long>(rt) * BM + row_in_tile;
+    for (TileIter it(P); it.valid(P); it.next(P), ++t) {
+      const int buf = t & 1;
+      const long long grow = static_cast<long long>(it.row_tile(P)) * BM + row_in_tile;
       const bool row_ok = grow < P.a;
       const float na = row_ok ? __ldg(P.nA + grow) : 0.f;
       const long long sym_row = P.symmetric ? grow : -1;
-      float acc[DP];
+      const long long col0 = static_cast<long long>(it.j) * BN;
+      const int cols_valid = static_cast<int>(min(static_cast<long long>(BN), P.b - col0));
+      mbar_wait(bar_vfull + 8 * vb, vph);
+      mbar_wait(bar_sfull + 8 * buf, (t >> 1) & 1u);
+      tcgen05_fence_after();
+      const float* Ns = nbuf + vb * NB_FLOATS;
+      const uint32_t tacc = tmem_base + tlane + static_cast<uint32_t>(buf ? TM_S1 : TM_S0);
+#pragma unroll 1
+      for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 16) {
+        if (DENSE && c0 >= cols_valid) break;
+        uint32_t r[16];
+        tmem_ld_32x16(tacc + static_cast<uint32_t>(c0), r);
+        tmem_wait_ld();
+        float kv[16];
 #pragma unroll
-      for (int c = 0; c < DP; ++c) acc[c] = 0.f;
-
-      for (int j = j0; j < j1; ++j) {
-        const long long col0 = static_cast<long long>(j) * BN;
-        const int cols_valid = static_cast<int>(min(static_cast<long long>(BN), P.b - col0));
-        mbar_wait(bar_vfull + 8 * vb, vph);
-        mbar_wait(bar_tfull + 8 * buf, (tph >> buf) & 1u);
-        tcgen05_fence_after();
-        const float* Vs = vbuf + vb * VBUF_FLOATS;
-        const float* Ns = nbuf + vb * BN;
-        const int cbeg = half * (BN / 2);
-        const int cend = min(cbeg + BN / 2, cols_valid);
-        const uint32_t tacc = tmem_base + tlane + static_cast<uint32_t>(buf * BN);
-        for (int c0 = cbeg; c0 < cend; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32(tacc + static_cast<uint32_t>(c0), r);
-          tmem_wait_ld();
-          const bool full_chunk = (c0 + 32 <= cend);
-          if (DENSE) {
-            float kv[32];
+        for (int c = 0; c < 16; ++c) {
+          const float nn = na + Ns[c0 + c];
+          float d2 = fmaf(P.m2g, __uint_as_float(r[c]), nn);
+          if (d2 < P.snap * nn || col0 + c0 + c == sym_row) d2 = 0.f;
+          kv[c] = kernel_value<KID>(d2, P.c0, DENSE ? 0.f : K_SCALE_LOG2);
+        }
+        if (DENSE) {
+          if (row_ok) {
+            float* dst = P.out + grow * P.ldo + col0 + c0;
+            if (c0 + 16 <= cols_valid && ((P.ldo & 3) == 0)) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float nn = na + Ns[c0 + c];
-              float d2 = fmaf(P.m2g, __uint_as_float(r[c]), nn);
-              if (d2 < P.snap * nn || col0 + c0 + c == sym_row) d2 = 0.f;
-              kv[c] = kernel_value<KID>(d2, P.c0);
+              for (int q = 0; q < 4; ++q)
+                reinterpret_cast<float4*>(dst)[q] =
+                    make_float4(kv[4 * q], kv[4 * q + 1], kv[4 * q + 2], kv[4 * q + 3]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; ++c)
+                if (c0 + c < cols_valid) dst[c] = kv[c];
             }
-            if (row_ok) {
-              float* dst = P.out + grow * P.ldo + col0 + c0;
-              if (full_chunk && ((P.ldo & 3) == 0)) {
+          }
+        } else {
+          // P = hi + 2^-11 lo, both fp16, packed two K-elements per 32-bit TMEM column
+          uint32_t w[16];
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                  reinterpret_cast<float4*>(dst)[q] =
-                      make_float4(kv[4 * q], kv[4 * q + 1], kv[4 * q + 2], kv[4 * q + 3]);
-              } else {
-#pragma unroll
-                for (int c = 0; c < 32; ++c)
-                  if (c0 + c < cend) dst[c] = kv[c];
-              }
-            }
+          for (int c = 0; c < 16; c += 2) {
+            const __half2 hi = __floats2half2_rn(kv[c], kv[c + 1]);
+            const float2 hf = __half22float2(hi);
+            const __half2 lo = __floats2half2_rn((kv[c] - hf.x) * LO_GAIN, (kv[c + 1] - hf.y) * LO_GAIN);
+            w[c / 2] = *reinterpret_cast<const uint32_t*>(&hi);
+            w[8 + c / 2] = *reinterpret_cast<const uint32_t*>(&lo);
+          }
+          tmem_st_32x16(tacc + static_cast<uint32_t>(c0), w);
+        }
+      }
+      if (!DENSE) tmem_wait_st();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_pready + 8 * buf);
+        mbar_arrive(bar_vempty + 8 * vb);
+      }
+      if (!DENSE && it.last()) {
+        if (half == 0) {
+          // the unit is complete once P V of its last tile has retired: read O out and add it
+          mbar_wait(bar_ofull, ophase);
+          tcgen05_fence_after();
+          uint32_t o1[NP], o2[NP];
+          if constexpr (NP == 32) {
+            tmem_ld_32x32(tmem_base + tlane + TM_O1, o1);
+            tmem_ld_32x32(tmem_base + tlane + TM_O2, o2);
           } else {
+            tmem_ld_32x16(tmem_base + tlane + TM_O1, o1);
+            tmem_ld_32x16(tmem_base + tlane + TM_O2, o2);
+          }
+          tmem_wait_ld();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_oempty);
+          if (row_ok) {
+            float* dst = P.out + grow * DP;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              if (full_chunk || (c0 + c < cend)) {
-                const float nn = na + Ns[c0 + c];
-                float d2 = fmaf(P.m2g, __uint_as_float(r[c]), nn);
-                if (d2 < P.snap * nn || col0 + c0 + c == sym_row) d2 = 0.f;
-                const float kv = kernel_value<KID>(d2, P.c0);
-                const float4* vrow = reinterpret_cast<const float4*>(Vs + (c0 + c) * DP);
-#pragma unroll
-                for (int q = 0; q < DP / 4; ++q) {
-                  const float4 v = vrow[q];
-                  acc[4 * q + 0] = fmaf(kv, v.x, acc[4 * q + 0]);
-                  acc[4 * q + 1] = fmaf(kv, v.y, acc[4 * q + 1]);
-                  acc[4 * q + 2] = fmaf(kv, v.z, acc[4 * q + 2]);
-                  acc[4 * q + 3] = fmaf(kv, v.w, acc[4 * q + 3]);
-                }
-              }
+            for (int c = 0; c < DP; ++c) {
+              const float v =
+                  fmaf(__uint_as_float(o2[c]), 1.f / LO_GAIN, __uint_as_float(o1[c])) * vinv[c];
+              red_add_f32(dst + c, v);
             }
           }
         }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar_tempty + 8 * buf);
-          mbar_arrive(bar_vempty + 8 * vb);
-        }
-        tph ^= (1u << buf);
-        buf ^= 1;
-        if (++vb == P.vbufs) { vb = 0; vph ^= 1; }
+        ophase ^= 1;
       }
-      if (!DENSE && row_ok) {
-        float* dst = P.out + grow * DP;
-#pragma unroll
-        for (int c = 0; c < DP; ++c) red_add_f32(dst + c, acc[c]);
-      }
+      if (++vb == P.vbufs) { vb = 0; vph ^= 1; }
     }
   }
 
@@ -326,6 +436,50 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// V pre-pass: per-column max |V|, then fp16 hi/lo tiles in the shared-memory layout of the P V MMA
+// ------------------------------------------------------------------------------------------------
+__global__ void colmax_kernel(const float* __restrict__ V, long long b, int dp,
+                              uint32_t* __restrict__ maxbits) {
+  // blockDim = (dp, rows): consecutive threads read consecutive floats of the row-major b x dp array
+  float m = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.y;
+  for (long long r = static_cast<long long>(blockIdx.x) * blockDim.y + threadIdx.y; r < b; r += stride)
+    m = fmaxf(m, fabsf(V[r * dp + threadIdx.x]));
+  atomicMax(maxbits + threadIdx.x, __float_as_uint(m));  // non-negative floats order like their bits
+}
+
+// one thread per 16-byte group = 8 consecutive K elements (rows of V) of one output column c
+__global__ void vsplit_kernel(const float* __restrict__ V, long long b, int dp, int np, long long tb,
+                              const uint32_t* __restrict__ maxbits, uint8_t* __restrict__ tiles) {
+  const long long groups_per_tile = static_cast<long long>(PV_STEPS) * np * 2;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= tb * groups_per_tile) return;
+  const long long tile = gid / groups_per_tile;
+  int rem = static_cast<int>(gid % groups_per_tile);
+  const int st = rem / (np * 2);
+  rem %= np * 2;
+  const int core = rem / 8;  // (n/8) * 2 + k/8
+  const int nn = rem % 8;
+  const int c = (core >> 1) * 8 + nn;
+  const int kh = core & 1;
+  float sc = 1.f, inv = 1.f;
+  if (c < dp) column_scale(maxbits[c], &sc, &inv);
+  __align__(16) __half hi[8];
+  __align__(16) __half lo[8];
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const long long row = tile * BN + st * UMMA_K + kh * 8 + kk;
+    const float v = (c < dp && row < b) ? V[row * dp + c] * sc : 0.f;
+    hi[kk] = __float2half_rn(v);
+    lo[kk] = __float2half_rn((v - __half2float(hi[kk])) * LO_GAIN);
+  }
+  const int tile_bytes = 2 * PV_STEPS * np * UMMA_K * 2;
+  uint8_t* base = tiles + tile * tile_bytes + st * (np * 32) + core * 128 + nn * 16;
+  *reinterpret_cast<uint4*>(base) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(base + tile_bytes / 2) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -449,9 +603,14 @@ static int launch_kid(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap
   return 2;
 }
 
+int64_t workspace_bytes(int64_t b, int dp) {
+  return WS_HEADER_BYTES + ceil_div(b > 0 ? b : 1, BN) * static_cast<int64_t>(vtile_bytes(dp));
+}
+
 int launch(void* stream, int kernel, float kscale, const void* A, const float* nA, int64_t a,
            int64_t lda, const void* B, const float* nB, int64_t b, int64_t ldb, int64_t p_pad,
-           const float* V, int dp, float* out, int64_t ldo, int symmetric, bool dense) {
+           const float* V, int dp, float* out, int64_t ldo, int symmetric, bool dense, void* ws,
+           int64_t ws_bytes) {
   SAB_REQUIRE(kernel >= 0 && kernel <= 3, "unknown kernel id %d", kernel);
   SAB_REQUIRE(a >= 0 && b >= 0, "negative row count");
   if (a == 0 || b == 0) return 0;
@@ -465,14 +624,19 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
               "operands must be 16-byte aligned");
   SAB_REQUIRE(a < (1ll << 31) && b < (1ll << 31), "row counts must fit in int32");
   if (!dense) {
-    SAB_REQUIRE(V != nullptr && (reinterpret_cast<uintptr_t>(V) & 15) == 0, "V must be 16-byte aligned");
+    SAB_REQUIRE(V != nullptr && out != nullptr, "V / out must not be NULL");
     SAB_REQUIRE(dp >= 4 && dp <= 32 && dp % 4 == 0, "dp must be a multiple of 4 in [4, 32], got %d", dp);
+    SAB_REQUIRE(ws != nullptr && (reinterpret_cast<uintptr_t>(ws) & 127) == 0 &&
+                    ws_bytes >= workspace_bytes(b, dp),
+                "workspace must be 128-byte aligned and hold sa_kmv_workspace_bytes(b, dp) = %lld bytes",
+                static_cast<long long>(workspace_bytes(b, dp)));
   } else {
     SAB_REQUIRE(ldo >= b, "ldo (%lld) < b (%lld)", static_cast<long long>(ldo), static_cast<long long>(b));
     SAB_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out must be 16-byte aligned");
   }
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   Params P;
   P.a = a;
@@ -484,13 +648,13 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   P.units = P.ta * P.nsplit;
   P.nA = nA;
   P.nB = nB;
-  P.V = V;
+  P.vws = static_cast<const uint8_t*>(ws);
   P.out = out;
   P.ldo = ldo;
   P.symmetric = symmetric;
   {
     const float steps = static_cast<float>(P.kblocks * (BK / UMMA_K));
-    const char* sv = std::getenv("SAB_SNAP");   // < 0 disables both corrections (calibration runs)
+    const char* sv = std::getenv("SAB_SNAP");  // < 0 disables both corrections (calibration runs)
     const float forced = sv ? static_cast<float>(std::atof(sv)) : 0.f;
     P.snap = sv ? forced : SNAP_PER_STEP * steps + SNAP_FLOOR;
     P.m2g = (sv && forced < 0.f) ? -2.f : -2.f * (1.f + ACC_BIAS_PER_STEP * steps);
@@ -501,8 +665,8 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   else P.c0 = kscale * 2.23606797749979f;
 
   // shared memory plan: as many pipeline stages as fit, two V buffers when they fit too
-  const int vbytes = (dense ? 0 : BN * dp * 4) + BN * 4;
-  const int fixed = 1024 /*alignment slack*/ + NUM_BARS * 8 + 64;
+  const int vbytes = (dense ? 0 : vtile_bytes(dp)) + NB_FLOATS * 4;
+  const int fixed = 32 * 4 /*vinv*/ + NUM_BARS * 8 + 64;
   int stages = env_int("SAB_STAGES", MAX_STAGES);
   int vbufs = env_int("SAB_VBUFS", 2);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -517,12 +681,26 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   P.stages = stages;
   P.vbufs = vbufs;
 
+  if (!dense) {
+    // V pre-pass: column maxima -> workspace header, then fp16 hi/lo tiles behind it
+    uint32_t* maxbits = static_cast<uint32_t*>(ws);
+    SAB_CHECK_CUDA(cudaMemsetAsync(ws, 0, WS_HEADER_BYTES, st));
+    const int rows = 512 / dp;
+    long long g = ceil_div(b, static_cast<int64_t>(rows) * 8);
+    if (g > 1184) g = 1184;
+    colmax_kernel<<<static_cast<int>(g), dim3(dp, rows), 0, st>>>(V, b, dp, maxbits);
+    const int np = pv_n(dp);
+    const long long groups = static_cast<long long>(P.tb) * PV_STEPS * np * 2;
+    vsplit_kernel<<<static_cast<int>(ceil_div(groups, 256)), 256, 0, st>>>(
+        V, b, dp, np, P.tb, maxbits, static_cast<uint8_t*>(ws) + WS_HEADER_BYTES);
+    SAB_CHECK_CUDA(cudaGetLastError());
+  }
+
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap(&tmA, A, a, p_pad, lda, BM)) return rc;
   if (int rc = make_tmap(&tmB, B, b, p_pad, ldb, BN)) return rc;
 
   const int grid = P.units < di.sms ? P.units : di.sms;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (kernel) {
     case SA_KERNEL_GAUSSIAN: return launch_kid<SA_KERNEL_GAUSSIAN>(st, tmA, tmB, P, grid, smem, dp, dense);
     case SA_KERNEL_LAPLACIAN: return launch_kid<SA_KERNEL_LAPLACIAN>(st, tmA, tmB, P, grid, smem, dp, dense);
@@ -542,18 +720,24 @@ int query_device(int* sms, int* smem) {
 }  // namespace kmv
 }  // namespace sab
 
+extern "C" int64_t sa_kmv_workspace_bytes(int64_t b, int dp) {
+  if (dp < 4 || dp > 32 || dp % 4 != 0) return -1;
+  return sab::kmv::workspace_bytes(b, dp);
+}
+
 extern "C" int sa_kmv(void* stream, int kernel, float kscale, const void* A, const float* nA,
                       int64_t a, int64_t lda, const void* B, const float* nB, int64_t b, int64_t ldb,
-                      int64_t p_pad, const float* V, int dp, float* out, int symmetric) {
+                      int64_t p_pad, const float* V, int dp, float* out, int symmetric, void* workspace,
+                      int64_t workspace_bytes) {
   return sab::kmv::launch(stream, kernel, kscale, A, nA, a, lda, B, nB, b, ldb, p_pad, V, dp, out, dp,
-                          symmetric, false);
+                          symmetric, false, workspace, workspace_bytes);
 }
 
 extern "C" int sa_kdense(void* stream, int kernel, float kscale, const void* A, const float* nA,
                          int64_t a, int64_t lda, const void* B, const float* nB, int64_t b,
                          int64_t ldb, int64_t p_pad, float* out, int64_t ldo, int symmetric) {
   return sab::kmv::launch(stream, kernel, kscale, A, nA, a, lda, B, nB, b, ldb, p_pad, nullptr, 4, out,
-                          ldo, symmetric, true);
+                          ldo, symmetric, true, nullptr, 0);
 }
 
 extern "C" int sa_device_info(int* sm_count, int* smem_bytes) {

@@ -49,7 +49,8 @@ class Falkon:
             if self.M > n:
                 warnings.warn(f"Number of centers M={self.M} exceeds the number of samples n={n}: using all samples")
             return np.arange(n, dtype=np.int64)
-        return np.sort(np.random.default_rng(self.seed).choice(n, size=self.M, replace=False))
+        seed = self.seed if self.seed is not None else self.options.center_seed
+        return np.sort(np.random.default_rng(seed).choice(n, size=self.M, replace=False))
 
     def _ops(self) -> CudaOps:
         return CudaOps(device=self.options.device, stage_rows=self.options.stage_rows)
@@ -105,8 +106,9 @@ class Falkon:
         counts = counts.cpu().numpy()
         offsets = np.concatenate([[0], np.cumsum(counts)])
         n_total = int(offsets[-1])
-        if self.seed is None and isinstance(self.center_selection, str):
-            raise ValueError("row_sharded fits need Falkon(seed=...) so that all ranks draw the same centres")
+        if self.seed is None and self.options.center_seed is None and isinstance(self.center_selection, str):
+            raise ValueError("row_sharded fits need Falkon(seed=...) or FalkonOptions(center_seed=...) so that "
+                             "all ranks draw the same centres")
         idx = self._select_centres(n_total)
         mine = idx[(idx >= offsets[comm.rank]) & (idx < offsets[comm.rank + 1])] - offsets[comm.rank]
         rows = ops.to_device(X[torch.from_numpy(mine).to(X.device)])

