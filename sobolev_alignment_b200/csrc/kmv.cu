@@ -85,6 +85,7 @@ struct Params {
   int nsplit;      // column chunks per row tile
   int units;       // ta * nsplit
   int stages, vbufs;
+  int csize;       // CTAs per cluster (1, or 2 = the pair shares every B tile through TMA multicast)
   const float* nA;
   const float* nB;
   const uint8_t* vws;  // workspace: header (column maxima) + fp16 V tiles
@@ -128,16 +129,19 @@ struct TileIter {
     j = j0;
   }
   __device__ __forceinline__ explicit TileIter(const Params& P)
-      : unit(static_cast<int>(blockIdx.x)), j(0), j0(0), j1(0) {
+      : unit(static_cast<int>(blockIdx.x) / P.csize), j(0), j0(0), j1(0) {
     if (unit < P.units) set_range(P);
   }
   __device__ __forceinline__ bool valid(const Params& P) const { return unit < P.units; }
   __device__ __forceinline__ bool first() const { return j == j0; }
   __device__ __forceinline__ bool last() const { return j + 1 == j1; }
-  __device__ __forceinline__ int row_tile(const Params& P) const { return unit / P.nsplit; }
+  // the CTAs of a cluster take adjacent row tiles of the same unit (and sweep the same column tiles)
+  __device__ __forceinline__ int row_tile(const Params& P, int crank) const {
+    return (unit / P.nsplit) * P.csize + crank;
+  }
   __device__ __forceinline__ void next(const Params& P) {
     if (++j == j1) {
-      unit += static_cast<int>(gridDim.x);
+      unit += static_cast<int>(gridDim.x) / P.csize;
       if (unit < P.units) set_range(P);
     }
   }
@@ -169,6 +173,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int crank = P.csize > 1 ? static_cast<int>(cluster_ctarank()) : 0;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) {
@@ -177,7 +182,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, P.csize);  // every CTA of the cluster must have drained the stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_sfull + 8 * i, 1);
@@ -205,6 +210,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
+  if (P.csize > 1) cluster_sync();  // peers' barriers are initialised before anything targets them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -214,14 +220,21 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       int s = 0;
       uint32_t ph = 0;
       for (TileIter it(P); it.valid(P); it.next(P)) {
-        const int rt = it.row_tile(P);
+        const int rt = it.row_tile(P, crank);
         for (int kb = 0; kb < P.kblocks; ++kb) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           const uint32_t full = bar_full + 8 * s;
           mbar_arrive_expect_tx(full, STAGE_BYTES);
           const uint32_t dstA = smem_u32(tiles + s * STAGE_BYTES);
           tma_load_2d(dstA, &tmA, full, kb * BK, rt * BM);
-          tma_load_2d(dstA + A_BYTES, &tmB, full, kb * BK, it.j * BN);
+          if (P.csize == 1) {
+            tma_load_2d(dstA + A_BYTES, &tmB, full, kb * BK, it.j * BN);
+          } else {
+            // each CTA of the pair fetches half of the B tile (112 rows = 14 whole swizzle atoms) and
+            // multicasts it into both CTAs' stage; both full barriers see all 28672 B bytes
+            tma_load_2d_mcast(dstA + A_BYTES + crank * (B_BYTES / 2), &tmB, full, kb * BK,
+                              it.j * BN + crank * (BN / 2), static_cast<uint16_t>(3));
+          }
           if (++s == P.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -248,7 +261,9 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             umma_f16_ss(tacc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
                         idesc_s, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(bar_empty + 8 * s);  // stage reusable once these MMAs retire
+          // stage reusable once these MMAs retire (in a cluster: tell the peer's producer too)
+          if (P.csize == 1) umma_commit(bar_empty + 8 * s);
+          else umma_commit_mcast(bar_empty + 8 * s, static_cast<uint16_t>(3));
           if (kb == P.kblocks - 1) umma_commit(bar_sfull + 8 * buf);
           if (++s == P.stages) { s = 0; ph ^= 1; }
         }
@@ -337,7 +352,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     uint32_t vph = 0;
     for (TileIter it(P); it.valid(P); it.next(P), ++t) {
       const int buf = t & 1;
-      const long long grow = static_cast<long long>(it.row_tile(P)) * BM + row_in_tile;
+      const long long grow = static_cast<long long>(it.row_tile(P, crank)) * BM + row_in_tile;
       const bool row_ok = grow < P.a;
       const float na = row_ok ? __ldg(P.nA + grow) : 0.f;
       const long long sym_row = P.symmetric ? grow : -1;
@@ -432,6 +447,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 
   tcgen05_fence_before();
   __syncthreads();
+  if (P.csize > 1) cluster_sync();  // no CTA leaves while its peer may still write into it
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -580,8 +596,24 @@ static int launch_inst(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMa
                        const Params& P, int grid, int smem) {
   auto kern = kmv_kernel<KID, DP, DENSE>;
   SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, THREADS, smem, st>>>(tmA, tmB, P);
-  SAB_CHECK_CUDA(cudaGetLastError());
+  if (P.csize == 1) {
+    kern<<<grid, THREADS, smem, st>>>(tmA, tmB, P);
+    SAB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = P.csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, P));
   return 0;
 }
 
@@ -644,8 +676,11 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   P.kblocks = static_cast<int>(p_pad / BK);
   P.ta = static_cast<int>(ceil_div(a, BM));
   P.tb = static_cast<int>(ceil_div(b, BN));
-  P.nsplit = dense ? 1 : choose_nsplit(P.ta, P.tb, di.sms, p_pad);
-  P.units = P.ta * P.nsplit;
+  // CTA pairs that share every B tile through TMA multicast (needs at least two row tiles)
+  P.csize = (env_int("SAB_CLUSTER", 2) >= 2 && P.ta >= 2 && di.sms >= 2) ? 2 : 1;
+  const int ta_units = static_cast<int>(ceil_div(P.ta, P.csize));
+  P.nsplit = dense ? 1 : choose_nsplit(ta_units, P.tb, di.sms / P.csize, p_pad * P.csize);
+  P.units = ta_units * P.nsplit;
   P.nA = nA;
   P.nB = nB;
   P.vws = static_cast<const uint8_t*>(ws);
@@ -698,9 +733,10 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
 
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap(&tmA, A, a, p_pad, lda, BM)) return rc;
-  if (int rc = make_tmap(&tmB, B, b, p_pad, ldb, BN)) return rc;
+  if (int rc = make_tmap(&tmB, B, b, p_pad, ldb, BN / P.csize)) return rc;
 
-  const int grid = P.units < di.sms ? P.units : di.sms;
+  const int clusters = P.units < di.sms / P.csize ? P.units : di.sms / P.csize;
+  const int grid = clusters * P.csize;
   switch (kernel) {
     case SA_KERNEL_GAUSSIAN: return launch_kid<SA_KERNEL_GAUSSIAN>(st, tmA, tmB, P, grid, smem, dp, dense);
     case SA_KERNEL_LAPLACIAN: return launch_kid<SA_KERNEL_LAPLACIAN>(st, tmA, tmB, P, grid, smem, dp, dense);
