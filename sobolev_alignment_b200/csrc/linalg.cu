@@ -269,29 +269,93 @@ diag_factor_kernel(float* __restrict__ A, long long lda, int k, float* __restric
 // --------------------------------------------------------------------------------------------
 // block triangular solves
 // --------------------------------------------------------------------------------------------
-// out[128 x DP] = op(T)[128x128] * x[128 x DP]; thread t owns row t%128 and half of the columns.
-template <int DP, bool TRANS>
-__device__ __forceinline__ void tile_times_rhs(const float* Ts, const float* xs, float (&acc)[DP / 2]) {
-  const int o = threadIdx.x & 127;
-  const int c0 = (threadIdx.x >> 7) * (DP / 2);
-#pragma unroll
-  for (int c = 0; c < DP / 2; ++c) acc[c] = 0.f;
-#pragma unroll 4
-  for (int l = 0; l < TS; ++l) {
-    const float t = TRANS ? Ts[l * LDD + o] : Ts[o * LDD + l];
-#pragma unroll
-    for (int c = 0; c < DP / 2; ++c) acc[c] = fmaf(t, xs[l * DP + c0 + c], acc[c]);
-  }
+// The 128x128 tile product out = op(T) x runs on the legacy tensor path (mma.sync m16n8k8 TF32) with
+// the 3xTF32 split (a = a_hi + a_lo, b = b_hi + b_lo; a_hi b_hi + a_lo b_hi + a_hi b_lo), which keeps
+// ~21 bits: the solve stays HBM / latency bound instead of shared-memory-broadcast bound.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-__device__ __forceinline__ void load_tile_128(const float* __restrict__ src, long long ld, float* Ts) {
-  for (int idx = threadIdx.x; idx < TS * TS / 4; idx += 256) {
+// shared-memory row strides chosen so that every fragment load is bank-conflict free
+__host__ __device__ constexpr int trsm_ldt(bool trans) { return trans ? TS + 8 : TS + 4; }
+__host__ __device__ constexpr int trsm_ldx(int nb8) { return nb8 == 1 ? 8 : (nb8 <= 3 ? 24 : 40); }
+
+// warp w owns output rows [16w, 16w+16); acc[nb] is the m16n8 fragment of column block nb
+template <int NB8, bool TRANS>
+__device__ __forceinline__ void tile_times_rhs(const float* Ts, const float* xs, float (&acc)[NB8][4]) {
+  constexpr int LT = trsm_ldt(TRANS);
+  constexpr int LX = trsm_ldx(NB8);
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = (threadIdx.x >> 5) * 16;
+  // three independent accumulator chains per column block (hi*hi, lo*hi, hi*lo) keep the dependent
+  // mma.sync chain at 16 instead of 48 on the critical path of the diagonal CTA
+  float c1[NB8][4], c2[NB8][4];
+#pragma unroll
+  for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[nb][i] = c1[nb][i] = c2[nb][i] = 0.f;
+#pragma unroll 4
+  for (int k0 = 0; k0 < TS; k0 += 8) {
+    float a[4];
+    if (TRANS) {
+      a[0] = Ts[(k0 + t) * LT + m0 + g];
+      a[1] = Ts[(k0 + t) * LT + m0 + g + 8];
+      a[2] = Ts[(k0 + t + 4) * LT + m0 + g];
+      a[3] = Ts[(k0 + t + 4) * LT + m0 + g + 8];
+    } else {
+      a[0] = Ts[(m0 + g) * LT + k0 + t];
+      a[1] = Ts[(m0 + g + 8) * LT + k0 + t];
+      a[2] = Ts[(m0 + g) * LT + k0 + t + 4];
+      a[3] = Ts[(m0 + g + 8) * LT + k0 + t + 4];
+    }
+    uint32_t ahi[4], alo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_tf32(a[i], ahi[i], alo[i]);
+#pragma unroll
+    for (int nb = 0; nb < NB8; ++nb) {
+      uint32_t bhi[2], blo[2];
+      split_tf32(xs[(k0 + t) * LX + nb * 8 + g], bhi[0], blo[0]);
+      split_tf32(xs[(k0 + t + 4) * LX + nb * 8 + g], bhi[1], blo[1]);
+      mma_tf32(acc[nb], ahi, bhi);
+      mma_tf32(c1[nb], alo, bhi);
+      mma_tf32(c2[nb], ahi, blo);
+    }
+  }
+#pragma unroll
+  for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[nb][i] += c1[nb][i] + c2[nb][i];
+}
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// all 16 128-bit requests of a thread are in flight at once (the solve is latency bound)
+template <bool TRANS>
+__device__ __forceinline__ void load_tile_128_async(const float* __restrict__ src, long long ld, float* Ts) {
+  constexpr int LT = trsm_ldt(TRANS);
+#pragma unroll
+  for (int i = 0; i < TS * TS / 4 / 256; ++i) {
+    const int idx = threadIdx.x + i * 256;
     const int r = idx >> 5, cq = idx & 31;
-    const float4 v = __ldcs(reinterpret_cast<const float4*>(src + static_cast<long long>(r) * ld + cq * 4));
-    Ts[r * LDD + cq * 4 + 0] = v.x;
-    Ts[r * LDD + cq * 4 + 1] = v.y;
-    Ts[r * LDD + cq * 4 + 2] = v.z;
-    Ts[r * LDD + cq * 4 + 3] = v.w;
+    cp_async_16(Ts + r * LT + cq * 4, src + static_cast<long long>(r) * ld + cq * 4);
   }
 }
 
@@ -302,44 +366,100 @@ template <int DP, bool TRANS>
 __global__ void __launch_bounds__(256)
 trsm_step_kernel(const float* __restrict__ L, long long ldl, const float* __restrict__ invdiag,
                  float* __restrict__ Bm, int k, int nblk) {
-  extern __shared__ float tsm[];
-  float* Ts = tsm;              // [128][129]
-  float* xs = tsm + TS * LDD;   // [128][DP]
+  constexpr int NB8 = (DP + 7) / 8;
+  constexpr int LT = trsm_ldt(TRANS);
+  constexpr int LX = trsm_ldx(NB8);
+  extern __shared__ __align__(16) float tsm[];
+  float* Ts = tsm;            // [128][LT]
+  float* xs = tsm + TS * LT;  // [128][LX]
   const int blk = TRANS ? static_cast<int>(blockIdx.x) : k + static_cast<int>(blockIdx.x);
   const int src = TRANS ? k + 1 : k - 1;  // block whose solution is being eliminated
   const bool has_update = TRANS ? (k + 1 < nblk) : (k > 0);
-  const int o = threadIdx.x & 127;
-  const int c0 = (threadIdx.x >> 7) * (DP / 2);
-  float* brow = Bm + (static_cast<long long>(blk) * TS + o) * DP + c0;
-  float bval[DP / 2];
-#pragma unroll
-  for (int c = 0; c < DP / 2; ++c) bval[c] = brow[c];
-
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = (threadIdx.x >> 5) * 16;
+  // Programmatic dependent launch: let the next step start its prologue now; everything that does
+  // not depend on the previous step (the L tile, the inverted diagonal block) is requested before
+  // waiting for that step to complete.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // padded columns of the rhs tile must be finite
+  if (LX > DP)
+    for (int idx = threadIdx.x; idx < TS * (LX - DP); idx += 256)
+      xs[(idx / (LX - DP)) * LX + DP + idx % (LX - DP)] = 0.f;
   if (has_update) {
     const float* tile = TRANS ? L + static_cast<long long>(src) * TS * ldl + static_cast<long long>(blk) * TS
                               : L + static_cast<long long>(blk) * TS * ldl + static_cast<long long>(src) * TS;
-    load_tile_128(tile, ldl, Ts);
-    const float* xsrc = Bm + static_cast<long long>(src) * TS * DP;
-    for (int idx = threadIdx.x; idx < TS * DP; idx += 256) xs[idx] = xsrc[idx];
-    __syncthreads();
-    float acc[DP / 2];
-    tile_times_rhs<DP, TRANS>(Ts, xs, acc);
+    load_tile_128_async<TRANS>(tile, ldl, Ts);
+  }
+  float4 inv[TS * TS / 4 / 256];
+  if (blk == k) {
+    const float* isrc = invdiag + static_cast<long long>(k) * TS * TS;
 #pragma unroll
-    for (int c = 0; c < DP / 2; ++c) bval[c] -= acc[c];
+    for (int i = 0; i < TS * TS / 4 / 256; ++i)
+      inv[i] = __ldg(reinterpret_cast<const float4*>(isrc) + threadIdx.x + i * 256);
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous step's x / b are now visible
+
+  // this thread's fragment of the block of b: rows m0+g and m0+g+8, columns nb*8 + 2t, +1
+  float* b0 = Bm + (static_cast<long long>(blk) * TS + m0 + g) * DP;
+  float* b1 = b0 + 8 * DP;
+  float bfrag[NB8][4];
+#pragma unroll
+  for (int nb = 0; nb < NB8; ++nb) {
+    const int c = nb * 8 + 2 * t;
+    float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+    if (c < DP) {
+      v0 = *reinterpret_cast<const float2*>(b0 + c);
+      v1 = *reinterpret_cast<const float2*>(b1 + c);
+    }
+    bfrag[nb][0] = v0.x; bfrag[nb][1] = v0.y; bfrag[nb][2] = v1.x; bfrag[nb][3] = v1.y;
+  }
+  if (has_update) {
+    const float* xsrc = Bm + static_cast<long long>(src) * TS * DP;
+    for (int idx = threadIdx.x; idx < TS * (DP / 4); idx += 256)
+      cp_async_16(xs + (idx / (DP / 4)) * LX + (idx % (DP / 4)) * 4, xsrc + idx * 4);
+  }
+  if (has_update) {
+    cp_async_wait_all();
+    __syncthreads();
+    float acc[NB8][4];
+    tile_times_rhs<NB8, TRANS>(Ts, xs, acc);
+#pragma unroll
+    for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bfrag[nb][i] -= acc[nb][i];
   }
   if (blk == k) {
-    __syncthreads();
-    load_tile_128(invdiag + static_cast<long long>(k) * TS * TS, TS, Ts);
+    __syncthreads();  // everyone is done with Ts / xs
 #pragma unroll
-    for (int c = 0; c < DP / 2; ++c) xs[o * DP + c0 + c] = bval[c];
-    __syncthreads();
-    float acc[DP / 2];
-    tile_times_rhs<DP, TRANS>(Ts, xs, acc);
+    for (int i = 0; i < TS * TS / 4 / 256; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      *reinterpret_cast<float4*>(Ts + (idx >> 5) * LT + (idx & 31) * 4) = inv[i];
+    }
 #pragma unroll
-    for (int c = 0; c < DP / 2; ++c) bval[c] = acc[c];
+    for (int nb = 0; nb < NB8; ++nb) {
+      const int c = nb * 8 + 2 * t;
+      xs[(m0 + g) * LX + c] = bfrag[nb][0];
+      xs[(m0 + g) * LX + c + 1] = bfrag[nb][1];
+      xs[(m0 + g + 8) * LX + c] = bfrag[nb][2];
+      xs[(m0 + g + 8) * LX + c + 1] = bfrag[nb][3];
+    }
+    __syncthreads();
+    float acc[NB8][4];
+    tile_times_rhs<NB8, TRANS>(Ts, xs, acc);
+#pragma unroll
+    for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bfrag[nb][i] = acc[nb][i];
   }
 #pragma unroll
-  for (int c = 0; c < DP / 2; ++c) brow[c] = bval[c];
+  for (int nb = 0; nb < NB8; ++nb) {
+    const int c = nb * 8 + 2 * t;
+    if (c < DP) {
+      *reinterpret_cast<float2*>(b0 + c) = make_float2(bfrag[nb][0], bfrag[nb][1]);
+      *reinterpret_cast<float2*>(b1 + c) = make_float2(bfrag[nb][2], bfrag[nb][3]);
+    }
+  }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -426,15 +546,30 @@ template <int DP>
 static int trsm_launch(cudaStream_t st, const float* L, long long M, long long ldl, const float* invdiag,
                        float* B, int transpose) {
   const int nblk = static_cast<int>(M / TS);
-  const int smem = (TS * LDD + TS * DP) * static_cast<int>(sizeof(float));
+  const int smem = (TS * trsm_ldt(transpose != 0) + TS * trsm_ldx((DP + 7) / 8)) * static_cast<int>(sizeof(float));
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (transpose) {
     auto kern = trsm_step_kernel<DP, true>;
     SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    for (int k = nblk - 1; k >= 0; --k) kern<<<k + 1, 256, smem, st>>>(L, ldl, invdiag, B, k, nblk);
+    for (int k = nblk - 1; k >= 0; --k) {
+      cfg.gridDim = dim3(k + 1);
+      SAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, L, ldl, invdiag, B, k, nblk));
+    }
   } else {
     auto kern = trsm_step_kernel<DP, false>;
     SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    for (int k = 0; k < nblk; ++k) kern<<<nblk - k, 256, smem, st>>>(L, ldl, invdiag, B, k, nblk);
+    for (int k = 0; k < nblk; ++k) {
+      cfg.gridDim = dim3(nblk - k);
+      SAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, L, ldl, invdiag, B, k, nblk));
+    }
   }
   SAB_CHECK_CUDA(cudaGetLastError());
   return 0;
