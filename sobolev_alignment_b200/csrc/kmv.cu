@@ -1,29 +1,35 @@
 // Fused kernel-matrix x matrix product for sm_100a:   out[a x dp] += k(A, B) @ V      (sa_kmv)
 // and the dense variant                               out[a x b]   = k(A, B)          (sa_kdense)
 //
-// One persistent CTA per SM, warp-specialised, two chained tensor-core products per tile (the
-// structure of a Blackwell attention kernel with the softmax replaced by the kernel function):
+// Persistent, warp-specialised, two chained tensor-core products per tile (the structure of a
+// Blackwell attention kernel with the softmax replaced by the kernel function).  The default
+// configuration runs the two SMs of a TPC as a `cta_group::2` pair (CG = 2): every tcgen05.mma covers
+// 256 rows (128 per CTA) x 224 columns, each CTA stages its own 128 x 64 tile of A and only HALF
+// (112 x 64) of the B tile, and the pair's tensor cores exchange the halves.  That cuts the bytes
+// delivered per SM and the tensor cores' shared-memory reads by a third against two independent CTAs
+// -- the L2 -> SM delivery rate, not the math, is what bounded the single-CTA kernel (profiles/).
 //
-//   warp 0      TMA producer: 128x64 tile of A and 224x64 tile of B (fp16, 128B swizzle) per stage
-//   warp 1      MMA issuer.  (1) S = A B^T: tcgen05.mma kind::f16 SS, M=128 N=224 K=16, fp32 in TMEM
-//               columns [0,224) / [224,448) (double buffered).  (2) O += P V: tcgen05.mma TS with the
-//               A operand P read straight from TMEM (where the epilogue wrote it over S) and the V
-//               tile from shared memory, accumulators O1/O2 in TMEM columns [448,480) / [480,512).
+//   warp 0      TMA producer (both CTAs): A tile + own half of the B tile (fp16, 128B swizzle) per
+//               stage; all complete_tx go to the LEADER CTA's full barrier
+//   warp 1      MMA issuer (leader CTA only).  (1) S = A B^T: tcgen05.mma kind::f16 SS, N=224, K=16,
+//               fp32 in TMEM columns [0,224) / [224,448) (double buffered).  (2) O += P V: tcgen05.mma
+//               TS with the A operand P read straight from TMEM (where the epilogue wrote it over S)
+//               and the V tile from shared memory, accumulators O1/O2 in columns [448,480)/[480,512).
 //   warp 2      TMEM allocator + bulk loader of the fp16 V tile and the B-norm tile
-//   warps 4-11  epilogue: tcgen05.ld 16 columns of S, d2 = |a|^2 + |b|^2 - 2 a.b, kernel function
-//               (sqrt / exp2 on the SFU), split k into fp16 hi + scaled fp16 lo, tcgen05.st both
-//               back over the S columns just read.  O is read out once per work unit and added to
-//               the output with red.global.add.
+//   warps 4-11  epilogue (both CTAs, own 128 rows): tcgen05.ld 16 columns of S,
+//               d2 = |a|^2 + |b|^2 - 2 a.b, kernel function (sqrt / exp2 on the SFU), split k into fp16
+//               hi + scaled fp16 lo, tcgen05.st both back over the S columns just read.  O is read out
+//               once per work unit and added to the output with red.global.add.
 //
 // K(A, B) only ever exists in TMEM and registers.  P and V are carried as hi + 2^-11 lo fp16 pairs
 // (three small MMAs per 16 columns: hi*hi -> O1, lo*hi + hi*lo -> O2), so the thin product keeps
 // ~22 bits although it runs on the fp16 tensor path; V is pre-scaled per column to the top of the
 // fp16 range by a tiny pre-pass (sa_kmv workspace).
 //
-// Work decomposition: units = row tiles x nsplit column chunks, round-robin over the CTAs with the
-// chunk index varying fastest: the CTAs running at the same time then cover only sms/nsplit row
-// tiles, so their A strips (128 x p fp16 each, re-read once per column tile) stay L2 resident while
-// CTAs on the same chunk sweep the same B tiles in step.
+// Work decomposition: units = (pairs of) row tiles x nsplit column chunks, round-robin over the CTA
+// pairs with the chunk index varying fastest: the pairs running at the same time then cover only
+// sms/(2 nsplit) row-tile pairs, so their A strips (re-read once per column tile) stay L2 resident
+// while pairs on the same chunk sweep the same B tiles in step.
 //
 // Replaces falkon `Kernel.mmv / dmmv / __call__` [external dependency of the reference], reached
 // from /root/reference/sobolev_alignment/krr_approx.py:227,314 and sobolev_alignment.py:950,955-958.
@@ -40,23 +46,25 @@
 namespace sab {
 namespace kmv {
 
-constexpr int BM = 128;
+constexpr int BM = 128;  // rows per CTA
 constexpr int BN = 224;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int A_BYTES = BM * BK * 2;            // 16384
-constexpr int B_BYTES = BN * BK * 2;            // 28672
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 45056 (multiple of 1024)
+constexpr int A_BYTES = BM * BK * 2;  // 16384
+constexpr int B_BYTES = BN * BK * 2;  // 28672 (each CTA of a pair stages half)
 constexpr int FIRST_EPI_WARP = 4;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;
+constexpr int KSUB = 2;        // 64-wide K blocks per pipeline stage: ONE tcgen05.commit per 8 MMAs.  Measured
+                               // (tools/mma_rate.cu): commits closer than ~580 cycles apart stall the tensor
+                               // pipe -- a commit per 4 MMAs (450 cycles) costs 30 % of the MMA rate
 constexpr int MAX_STAGES = 4;
 constexpr int TMEM_COLS = 512;
 constexpr int TM_S0 = 0, TM_S1 = BN, TM_O1 = 2 * BN, TM_O2 = 2 * BN + 32;
 constexpr int PV_STEPS = BN / UMMA_K;  // 14
 constexpr int HALF_COLS = BN / 2;      // 112 columns per epilogue warp
 constexpr int NB_FLOATS = 256;         // shared-memory slot of the B-norm tile
-constexpr int NUM_BARS = 18;
+constexpr int NUM_BARS = 2 * MAX_STAGES + 10;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float K_SCALE_LOG2 = 14.f;   // k values are carried as k * 2^14 in fp16
 constexpr float LO_GAIN = 2048.f;      // the fp16 residual is carried as (x - hi) * 2^11
@@ -74,18 +82,22 @@ constexpr float ACC_BIAS_PER_STEP = 0.8e-7f;
 constexpr float SNAP_PER_STEP = 0.3e-7f;
 constexpr float SNAP_FLOOR = 4.0e-7f;
 
-__host__ __device__ constexpr int pv_n(int dp) { return dp <= 16 ? 16 : 32; }
-// bytes of one V tile in the workspace / in shared memory: hi block + lo block
-__host__ __device__ constexpr int vtile_bytes(int dp) { return 2 * PV_STEPS * pv_n(dp) * UMMA_K * 2; }
+// bytes one CTA stages per 64-wide K block (its A tile + its share of the B tile) / per pipeline stage
+__host__ __device__ constexpr int sub_bytes(int cg) { return A_BYTES + B_BYTES / cg; }
+__host__ __device__ constexpr int stage_bytes(int cg) { return KSUB * sub_bytes(cg); }
+// N of the P V product (columns of V incl. padding); the 2-CTA TS form needs a multiple of 32
+__host__ __device__ constexpr int pv_n(int dp, int cg) { return (cg == 2 || dp > 16) ? 32 : 16; }
+// bytes of one V tile in the workspace: per CTA of the group a hi block followed by a lo block,
+// each PV_STEPS x (pv_n / cg) x 16 fp16
+__host__ __device__ constexpr int vtile_bytes(int dp, int cg) { return 2 * PV_STEPS * pv_n(dp, cg) * UMMA_K * 2; }
 
 struct Params {
   long long a, b;  // rows of A / rows of B
   int kblocks;     // p_pad / 64
   int ta, tb;      // row tiles, column tiles
   int nsplit;      // column chunks per row tile
-  int units;       // ta * nsplit
+  int units;       // ceil(ta / CG) * nsplit
   int stages, vbufs;
-  int csize;       // CTAs per cluster (1, or 2 = the pair shares every B tile through TMA multicast)
   const float* nA;
   const float* nB;
   const uint8_t* vws;  // workspace: header (column maxima) + fp16 V tiles
@@ -95,6 +107,8 @@ struct Params {
   float snap;  // squared distances below snap * (|a|^2 + |b|^2) are treated as exactly zero
   float m2g;   // -2 * (1 + accumulator-bias compensation)
   int symmetric;
+  int debug;   // SAB_DEBUG bit mask, timing experiments only (results are garbage): 1 = no TMA
+               // loads after the first fill, 2 = epilogue skips its math, 4 = no P V products
 };
 
 // k(d2) * 2^shift  (shift = 14 for the fused product so that k fills the fp16 range, 0 for dense)
@@ -119,7 +133,8 @@ __device__ __forceinline__ void column_scale(uint32_t maxbits, float* scale, flo
   *inv = __uint_as_float(static_cast<uint32_t>(e - 13 + 127) << 23);
 }
 
-// iterates the (unit, column tile) pairs this CTA owns, in execution order
+// iterates the (unit, column tile) pairs this CTA (pair) owns, in execution order
+template <int CG>
 struct TileIter {
   int unit, j, j0, j1;
   __device__ __forceinline__ void set_range(const Params& P) {
@@ -129,51 +144,61 @@ struct TileIter {
     j = j0;
   }
   __device__ __forceinline__ explicit TileIter(const Params& P)
-      : unit(static_cast<int>(blockIdx.x) / P.csize), j(0), j0(0), j1(0) {
+      : unit(static_cast<int>(blockIdx.x) / CG), j(0), j0(0), j1(0) {
     if (unit < P.units) set_range(P);
   }
   __device__ __forceinline__ bool valid(const Params& P) const { return unit < P.units; }
   __device__ __forceinline__ bool first() const { return j == j0; }
   __device__ __forceinline__ bool last() const { return j + 1 == j1; }
-  // the CTAs of a cluster take adjacent row tiles of the same unit (and sweep the same column tiles)
+  // the CTAs of a pair take adjacent row tiles of the same unit (and sweep the same column tiles)
   __device__ __forceinline__ int row_tile(const Params& P, int crank) const {
-    return (unit / P.nsplit) * P.csize + crank;
+    return (unit / P.nsplit) * CG + crank;
   }
   __device__ __forceinline__ void next(const Params& P) {
     if (++j == j1) {
-      unit += static_cast<int>(gridDim.x) / P.csize;
+      unit += static_cast<int>(gridDim.x) / CG;
       if (unit < P.units) set_range(P);
     }
   }
 };
 
-template <int KID, int DP, bool DENSE>
+template <int KID, int DP, bool DENSE, int CG>
 __global__ void __launch_bounds__(THREADS, 1)
 kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
            const Params P) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int NP = pv_n(DP);
-  constexpr int VT_BYTES = DENSE ? 0 : vtile_bytes(DP);
+  constexpr int NP = pv_n(DP, CG);          // columns of the O accumulators
+  constexpr int NPC = NP / CG;              // V columns staged by this CTA
+  constexpr int STAGE = stage_bytes(CG);
+  constexpr int SUB = sub_bytes(CG);
+  constexpr int VT_BYTES = DENSE ? 0 : vtile_bytes(DP, CG) / CG;  // this CTA's share of a V tile
   constexpr int VLO_OFF = VT_BYTES / 2;
+  constexpr uint16_t PAIR_MASK = 3;         // cluster = exactly the CTA pair
+  using Iter = TileIter<CG>;
   uint8_t* tiles = smem;
-  uint8_t* vbuf = tiles + P.stages * STAGE_BYTES;
+  uint8_t* vbuf = tiles + P.stages * STAGE;
   float* nbuf = reinterpret_cast<float*>(vbuf + P.vbufs * VT_BYTES);
   float* vinv = nbuf + P.vbufs * NB_FLOATS;  // [32] 2^-14 / column scale
   uint64_t* bars = reinterpret_cast<uint64_t*>(vinv + 32);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
 
-  const uint32_t bar_full = smem_u32(bars + 0);     // [4] TMA -> MMA
-  const uint32_t bar_empty = smem_u32(bars + 4);    // [4] MMA -> TMA
-  const uint32_t bar_sfull = smem_u32(bars + 8);    // [2] S accumulator ready -> epilogue
-  const uint32_t bar_pready = smem_u32(bars + 10);  // [2] epilogue wrote P (dense: drained S) -> MMA
-  const uint32_t bar_vfull = smem_u32(bars + 12);   // [2] V / norm tile landed
-  const uint32_t bar_vempty = smem_u32(bars + 14);  // [2] V / norm tile consumed
-  const uint32_t bar_ofull = smem_u32(bars + 16);   // O accumulators of a unit complete
-  const uint32_t bar_oempty = smem_u32(bars + 17);  // O accumulators read out
+  const uint32_t bar_full = smem_u32(bars + 0);                      // [8] TMA -> MMA (leader's are used)
+  const uint32_t bar_empty = smem_u32(bars + MAX_STAGES);            // [8] MMA -> TMA (each CTA its own)
+  const uint32_t bar_sfull = smem_u32(bars + 2 * MAX_STAGES + 0);    // [2] S accumulator ready -> epilogue
+  const uint32_t bar_pready = smem_u32(bars + 2 * MAX_STAGES + 2);   // [2] epilogues wrote P (dense: drained S) -> MMA (leader's)
+  const uint32_t bar_vfull = smem_u32(bars + 2 * MAX_STAGES + 4);    // [2] V / norm tile landed
+  const uint32_t bar_vempty = smem_u32(bars + 2 * MAX_STAGES + 6);   // [2] V / norm tile consumed
+  const uint32_t bar_ofull = smem_u32(bars + 2 * MAX_STAGES + 8);    // O accumulators of a unit complete
+  const uint32_t bar_oempty = smem_u32(bars + 2 * MAX_STAGES + 9);   // O accumulators read out (leader's)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int crank = P.csize > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int crank = CG > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = crank == 0;
+  // barriers the peer CTA signals live in the leader's shared memory
+  const uint32_t lead_full = CG > 1 ? mapa_shared(bar_full, 0) : bar_full;
+  const uint32_t lead_pready = CG > 1 ? mapa_shared(bar_pready, 0) : bar_pready;
+  const uint32_t lead_oempty = CG > 1 ? mapa_shared(bar_oempty, 0) : bar_oempty;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) {
@@ -181,17 +206,17 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       __trap();
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, P.csize);  // every CTA of the cluster must have drained the stage
+      mbar_init(bar_full + 8 * s, 1);   // the leader producer's arrive.expect_tx (covers both CTAs' bytes)
+      mbar_init(bar_empty + 8 * s, 1);  // one tcgen05.commit (delivered to both CTAs of a pair)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_sfull + 8 * i, 1);
-      mbar_init(bar_pready + 8 * i, EPI_WARPS);
+      mbar_init(bar_pready + 8 * i, CG * EPI_WARPS);
       mbar_init(bar_vfull + 8 * i, 1);
       mbar_init(bar_vempty + 8 * i, DENSE ? EPI_WARPS : EPI_WARPS + 1);
     }
     mbar_init(bar_ofull, 1);
-    mbar_init(bar_oempty, EPI_WARPS / 2);
+    mbar_init(bar_oempty, CG * (EPI_WARPS / 2));
     fence_barrier_init();
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
@@ -204,13 +229,13 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     vinv[threadIdx.x] = inv * 6.103515625e-05f;  // 2^-14: undo the scaling of k as well
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc<CG>(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_relinquish<CG>();
   }
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
-  if (P.csize > 1) cluster_sync();  // peers' barriers are initialised before anything targets them
+  if (CG > 1) cluster_sync();  // the peer's barriers are initialised before anything targets them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -219,66 +244,77 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (TileIter it(P); it.valid(P); it.next(P)) {
+      bool filled = false;
+      for (Iter it(P); it.valid(P); it.next(P)) {
         const int rt = it.row_tile(P, crank);
-        for (int kb = 0; kb < P.kblocks; ++kb) {
+        for (int kb = 0; kb < P.kblocks; kb += KSUB) {
+          const int nsub = min(KSUB, P.kblocks - kb);
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          const uint32_t full = bar_full + 8 * s;
-          mbar_arrive_expect_tx(full, STAGE_BYTES);
-          const uint32_t dstA = smem_u32(tiles + s * STAGE_BYTES);
-          tma_load_2d(dstA, &tmA, full, kb * BK, rt * BM);
-          if (P.csize == 1) {
-            tma_load_2d(dstA + A_BYTES, &tmB, full, kb * BK, it.j * BN);
+          const uint32_t dst = smem_u32(tiles + s * STAGE);
+          if ((P.debug & 1) && filled) {  // timing experiment: the stages keep their first contents
+            if (leader) mbar_arrive(bar_full + 8 * s);
+          } else if constexpr (CG == 1) {
+            const uint32_t full = bar_full + 8 * s;
+            mbar_arrive_expect_tx(full, nsub * SUB);
+            for (int u = 0; u < nsub; ++u) {
+              tma_load_2d(dst + u * SUB, &tmA, full, (kb + u) * BK, rt * BM);
+              tma_load_2d(dst + u * SUB + A_BYTES, &tmB, full, (kb + u) * BK, it.j * BN);
+            }
           } else {
-            // each CTA of the pair fetches half of the B tile (112 rows = 14 whole swizzle atoms) and
-            // multicasts it into both CTAs' stage; both full barriers see all 28672 B bytes
-            tma_load_2d_mcast(dstA + A_BYTES + crank * (B_BYTES / 2), &tmB, full, kb * BK,
-                              it.j * BN + crank * (BN / 2), static_cast<uint16_t>(3));
+            // both CTAs fill their own stage; every byte is accounted on the leader's full barrier
+            if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, CG * nsub * SUB);
+            const uint32_t full = lead_full + 8 * s;
+            for (int u = 0; u < nsub; ++u) {
+              tma_load_2d_cg2(dst + u * SUB, &tmA, full, (kb + u) * BK, rt * BM);
+              tma_load_2d_cg2(dst + u * SUB + A_BYTES, &tmB, full, (kb + u) * BK,
+                              it.j * BN + crank * (BN / CG));
+            }
           }
-          if (++s == P.stages) { s = 0; ph ^= 1; }
+          if (++s == P.stages) { s = 0; ph ^= 1; filled = true; }
         }
       }
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(BM, BN);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(BM, NP);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(BM * CG, BN);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(BM * CG, NP);
       int s = 0;
       uint32_t ph = 0;
       // S = A B^T for one column tile into accumulator `buf`
       auto issue_s = [&](int buf) {
         const uint32_t tacc = tmem_base + static_cast<uint32_t>(buf ? TM_S1 : TM_S0);
-        for (int kb = 0; kb < P.kblocks; ++kb) {
+        for (int kb = 0; kb < P.kblocks; kb += KSUB) {
+          const int nsub = min(KSUB, P.kblocks - kb);
           mbar_wait(bar_full + 8 * s, ph);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES);
-          const uint64_t da = umma_smem_desc_sw128(sa);
-          const uint64_t db = umma_smem_desc_sw128(sa + A_BYTES);
+          const uint32_t sa = smem_u32(tiles + s * STAGE);
+          for (int u = 0; u < nsub; ++u) {
+            const uint64_t da = umma_smem_desc_sw128(sa + u * SUB);
+            const uint64_t db = umma_smem_desc_sw128(sa + u * SUB + A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 fp16 = 32 B along K inside the 128 B swizzle atom: +2 in 16-byte units
-            umma_f16_ss(tacc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                        idesc_s, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 fp16 = 32 B along K inside the 128 B swizzle atom: +2 in 16-byte units
+              umma_f16_ss<CG>(tacc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                              idesc_s, (kb | u | k) != 0 ? 1u : 0u);
+            }
           }
-          // stage reusable once these MMAs retire (in a cluster: tell the peer's producer too)
-          if (P.csize == 1) umma_commit(bar_empty + 8 * s);
-          else umma_commit_mcast(bar_empty + 8 * s, static_cast<uint16_t>(3));
-          if (kb == P.kblocks - 1) umma_commit(bar_sfull + 8 * buf);
+          umma_commit<CG>(bar_empty + 8 * s, PAIR_MASK);  // stage reusable once these MMAs retire
+          if (kb + KSUB >= P.kblocks) umma_commit<CG>(bar_sfull + 8 * buf, PAIR_MASK);
           if (++s == P.stages) { s = 0; ph ^= 1; }
         }
       };
 
       if (DENSE) {
         uint32_t t = 0;
-        for (TileIter it(P); it.valid(P); it.next(P), ++t) {
+        for (Iter it(P); it.valid(P); it.next(P), ++t) {
           const int buf = t & 1;
-          mbar_wait(bar_pready + 8 * buf, ((t >> 1) & 1u) ^ 1u);  // epilogue drained this buffer
+          mbar_wait_cluster(bar_pready + 8 * buf, ((t >> 1) & 1u) ^ 1u);  // epilogues drained this buffer
           tcgen05_fence_after();
           issue_s(buf);
         }
       } else {
-        TileIter ahead(P), cur(P);
+        Iter ahead(P), cur(P);
         // the S product runs two tiles ahead of the P V product
         if (ahead.valid(P)) { issue_s(0); ahead.next(P); }
         if (ahead.valid(P)) { issue_s(1); ahead.next(P); }
@@ -287,30 +323,32 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         uint32_t vph = 0;
         for (; cur.valid(P); cur.next(P), ++t) {
           const int buf = t & 1;
-          mbar_wait(bar_pready + 8 * buf, (t >> 1) & 1u);  // P(t) is in TMEM
-          mbar_wait(bar_vfull + 8 * vb, vph);              // V(t) is in shared memory
-          if (cur.first() && t != 0) {                     // previous unit's O has been read out
-            mbar_wait(bar_oempty, ophase);
+          // P(t) is in TMEM of both CTAs; every epilogue warp waited for its V(t) / norm tile before
+          // writing P, so the V tiles of both CTAs have landed as well
+          mbar_wait_cluster(bar_pready + 8 * buf, (t >> 1) & 1u);
+          if (CG == 1) mbar_wait(bar_vfull + 8 * vb, vph);
+          if (cur.first() && t != 0) {  // previous unit's O has been read out
+            mbar_wait_cluster(bar_oempty, ophase);
             ophase ^= 1;
           }
           tcgen05_fence_after();
           const uint32_t tp = tmem_base + static_cast<uint32_t>(buf ? TM_S1 : TM_S0);
           const uint32_t vs = smem_u32(vbuf + vb * VT_BYTES);
 #pragma unroll
-          for (int st = 0; st < PV_STEPS; ++st) {
-            // V tile: per 16-column step NP x 16 fp16, 8x8 core matrices, K-major, no swizzle:
+          for (int st = 0; st < ((P.debug & 4) ? 0 : PV_STEPS); ++st) {
+            // V tile: per 16-column step NPC x 16 fp16, 8x8 core matrices, K-major, no swizzle:
             // core (n/8, k/8) at ((n/8)*2 + k/8) * 128 B  ->  LBO (K) = 128 B, SBO (N) = 256 B
-            const uint64_t dhi = umma_smem_desc_noswz(vs + st * (NP * 32), 128, 256);
-            const uint64_t dlo = umma_smem_desc_noswz(vs + VLO_OFF + st * (NP * 32), 128, 256);
+            const uint64_t dhi = umma_smem_desc_noswz(vs + st * (NPC * 32), 128, 256);
+            const uint64_t dlo = umma_smem_desc_noswz(vs + VLO_OFF + st * (NPC * 32), 128, 256);
             const uint32_t phi = tp + static_cast<uint32_t>(16 * st);  // 8 columns = 16 fp16 of hi
             const uint32_t plo = phi + 8;                               // then 8 columns of lo
             const uint32_t acc = (cur.first() && st == 0) ? 0u : 1u;
-            umma_f16_ts(tmem_base + TM_O1, phi, dhi, idesc_pv, acc);
-            umma_f16_ts(tmem_base + TM_O2, plo, dhi, idesc_pv, acc);
-            umma_f16_ts(tmem_base + TM_O2, phi, dlo, idesc_pv, 1u);
+            umma_f16_ts<CG>(tmem_base + TM_O1, phi, dhi, idesc_pv, acc);
+            umma_f16_ts<CG>(tmem_base + TM_O2, plo, dhi, idesc_pv, acc);
+            umma_f16_ts<CG>(tmem_base + TM_O2, phi, dlo, idesc_pv, 1u);
           }
-          umma_commit(bar_vempty + 8 * vb);
-          if (cur.last()) umma_commit(bar_ofull);
+          umma_commit<CG>(bar_vempty + 8 * vb, PAIR_MASK);
+          if (cur.last()) umma_commit<CG>(bar_ofull, PAIR_MASK);
           if (ahead.valid(P)) {  // S(t+2) reuses the TMEM columns of P(t): in issue order behind P V(t)
             issue_s(buf);
             ahead.next(P);
@@ -324,7 +362,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     if (lane == 0) {
       int vb = 0;
       uint32_t vph = 0;
-      for (TileIter it(P); it.valid(P); it.next(P)) {
+      for (Iter it(P); it.valid(P); it.next(P)) {
         mbar_wait(bar_vempty + 8 * vb, vph ^ 1);
         const long long col0 = static_cast<long long>(it.j) * BN;
         const int cols_valid = static_cast<int>(min(static_cast<long long>(BN), P.b - col0));
@@ -334,7 +372,8 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         bulk_load_1d(smem_u32(nbuf + vb * NB_FLOATS), P.nB + col0, nbytes, full);
         if (!DENSE)
           bulk_load_1d(smem_u32(vbuf + vb * VT_BYTES),
-                       P.vws + WS_HEADER_BYTES + static_cast<long long>(it.j) * VT_BYTES, VT_BYTES, full);
+                       P.vws + WS_HEADER_BYTES + (static_cast<long long>(it.j) * CG + crank) * VT_BYTES,
+                       VT_BYTES, full);
         if (++vb == P.vbufs) { vb = 0; vph ^= 1; }
       }
     }
@@ -350,7 +389,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     uint32_t t = 0, ophase = 0;
     int vb = 0;
     uint32_t vph = 0;
-    for (TileIter it(P); it.valid(P); it.next(P), ++t) {
+    for (Iter it(P); it.valid(P); it.next(P), ++t) {
       const int buf = t & 1;
       const long long grow = static_cast<long long>(it.row_tile(P, crank)) * BM + row_in_tile;
       const bool row_ok = grow < P.a;
@@ -365,7 +404,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       const uint32_t tacc = tmem_base + tlane + static_cast<uint32_t>(buf ? TM_S1 : TM_S0);
 #pragma unroll 1
       for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 16) {
-        if (DENSE && c0 >= cols_valid) break;
+        if ((DENSE && c0 >= cols_valid) || (P.debug & 2)) break;
         uint32_t r[16];
         tmem_ld_32x16(tacc + static_cast<uint32_t>(c0), r);
         tmem_wait_ld();
@@ -409,7 +448,8 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(bar_pready + 8 * buf);
+        if (CG == 1) mbar_arrive(bar_pready + 8 * buf);
+        else mbar_arrive_cluster(lead_pready + 8 * buf);
         mbar_arrive(bar_vempty + 8 * vb);
       }
       if (!DENSE && it.last()) {
@@ -428,7 +468,10 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           tmem_wait_ld();
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_oempty);
+          if (lane == 0) {
+            if (CG == 1) mbar_arrive(bar_oempty);
+            else mbar_arrive_cluster(lead_oempty);
+          }
           if (row_ok) {
             float* dst = P.out + grow * DP;
 #pragma unroll
@@ -447,10 +490,10 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 
   tcgen05_fence_before();
   __syncthreads();
-  if (P.csize > 1) cluster_sync();  // no CTA leaves while its peer may still write into it
+  if (CG > 1) cluster_sync();  // no CTA leaves (or frees TMEM) while its peer may still use it
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc<CG>(tmem_base, TMEM_COLS);
   }
 }
 
@@ -467,8 +510,10 @@ __global__ void colmax_kernel(const float* __restrict__ V, long long b, int dp,
   atomicMax(maxbits + threadIdx.x, __float_as_uint(m));  // non-negative floats order like their bits
 }
 
-// one thread per 16-byte group = 8 consecutive K elements (rows of V) of one output column c
-__global__ void vsplit_kernel(const float* __restrict__ V, long long b, int dp, int np, long long tb,
+// one thread per 16-byte group = 8 consecutive K elements (rows of V) of one output column c.
+// Tile layout: for each CTA r of the group [hi block | lo block], each PV_STEPS x (np / cg) x 16 fp16
+// as K-major 8x8 core matrices; CTA r holds the columns [r np/cg, (r+1) np/cg).
+__global__ void vsplit_kernel(const float* __restrict__ V, long long b, int dp, int np, int cg, long long tb,
                               const uint32_t* __restrict__ maxbits, uint8_t* __restrict__ tiles) {
   const long long groups_per_tile = static_cast<long long>(PV_STEPS) * np * 2;
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -477,7 +522,7 @@ __global__ void vsplit_kernel(const float* __restrict__ V, long long b, int dp, 
   int rem = static_cast<int>(gid % groups_per_tile);
   const int st = rem / (np * 2);
   rem %= np * 2;
-  const int core = rem / 8;  // (n/8) * 2 + k/8
+  const int core = rem / 8;  // (n/8) * 2 + k/8 over the full np columns
   const int nn = rem % 8;
   const int c = (core >> 1) * 8 + nn;
   const int kh = core & 1;
@@ -492,10 +537,14 @@ __global__ void vsplit_kernel(const float* __restrict__ V, long long b, int dp, 
     hi[kk] = __float2half_rn(v);
     lo[kk] = __float2half_rn((v - __half2float(hi[kk])) * LO_GAIN);
   }
+  const int npc = np / cg;
+  const int r = c / npc, cl = c % npc;
   const int tile_bytes = 2 * PV_STEPS * np * UMMA_K * 2;
-  uint8_t* base = tiles + tile * tile_bytes + st * (np * 32) + core * 128 + nn * 16;
+  const int cta_bytes = tile_bytes / cg;
+  const int core_local = (cl >> 3) * 2 + kh;
+  uint8_t* base = tiles + tile * tile_bytes + r * cta_bytes + st * (npc * 32) + core_local * 128 + nn * 16;
   *reinterpret_cast<uint4*>(base) = *reinterpret_cast<const uint4*>(hi);
-  *reinterpret_cast<uint4*>(base + tile_bytes / 2) = *reinterpret_cast<const uint4*>(lo);
+  *reinterpret_cast<uint4*>(base + cta_bytes / 2) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -591,12 +640,12 @@ static int choose_nsplit(int ta, int tb, int sms, long long p_pad) {
   return best_ns;
 }
 
-template <int KID, int DP, bool DENSE>
+template <int KID, int DP, bool DENSE, int CG>
 static int launch_inst(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB,
                        const Params& P, int grid, int smem) {
-  auto kern = kmv_kernel<KID, DP, DENSE>;
+  auto kern = kmv_kernel<KID, DP, DENSE, CG>;
   SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  if (P.csize == 1) {
+  if (CG == 1) {
     kern<<<grid, THREADS, smem, st>>>(tmA, tmB, P);
     SAB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -608,7 +657,7 @@ static int launch_inst(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMa
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = P.csize;
+  attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -617,26 +666,39 @@ static int launch_inst(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMa
   return 0;
 }
 
-template <int KID>
+template <int KID, int CG>
 static int launch_kid(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB,
                       const Params& P, int grid, int smem, int dp, bool dense) {
-  if (dense) return launch_inst<KID, 4, true>(st, tmA, tmB, P, grid, smem);
+  if (dense) return launch_inst<KID, 4, true, CG>(st, tmA, tmB, P, grid, smem);
   switch (dp) {
-    case 4: return launch_inst<KID, 4, false>(st, tmA, tmB, P, grid, smem);
-    case 8: return launch_inst<KID, 8, false>(st, tmA, tmB, P, grid, smem);
-    case 12: return launch_inst<KID, 12, false>(st, tmA, tmB, P, grid, smem);
-    case 16: return launch_inst<KID, 16, false>(st, tmA, tmB, P, grid, smem);
-    case 20: return launch_inst<KID, 20, false>(st, tmA, tmB, P, grid, smem);
-    case 24: return launch_inst<KID, 24, false>(st, tmA, tmB, P, grid, smem);
-    case 28: return launch_inst<KID, 28, false>(st, tmA, tmB, P, grid, smem);
-    case 32: return launch_inst<KID, 32, false>(st, tmA, tmB, P, grid, smem);
+    case 4: return launch_inst<KID, 4, false, CG>(st, tmA, tmB, P, grid, smem);
+    case 8: return launch_inst<KID, 8, false, CG>(st, tmA, tmB, P, grid, smem);
+    case 12: return launch_inst<KID, 12, false, CG>(st, tmA, tmB, P, grid, smem);
+    case 16: return launch_inst<KID, 16, false, CG>(st, tmA, tmB, P, grid, smem);
+    case 20: return launch_inst<KID, 20, false, CG>(st, tmA, tmB, P, grid, smem);
+    case 24: return launch_inst<KID, 24, false, CG>(st, tmA, tmB, P, grid, smem);
+    case 28: return launch_inst<KID, 28, false, CG>(st, tmA, tmB, P, grid, smem);
+    case 32: return launch_inst<KID, 32, false, CG>(st, tmA, tmB, P, grid, smem);
   }
   set_error("dp must be a multiple of 4 in [4, 32], got %d", dp);
   return 2;
 }
 
+template <int CG>
+static int launch_cg(cudaStream_t st, int kernel, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                     const Params& P, int grid, int smem, int dp, bool dense) {
+  switch (kernel) {
+    case SA_KERNEL_GAUSSIAN: return launch_kid<SA_KERNEL_GAUSSIAN, CG>(st, tmA, tmB, P, grid, smem, dp, dense);
+    case SA_KERNEL_LAPLACIAN: return launch_kid<SA_KERNEL_LAPLACIAN, CG>(st, tmA, tmB, P, grid, smem, dp, dense);
+    case SA_KERNEL_MATERN15: return launch_kid<SA_KERNEL_MATERN15, CG>(st, tmA, tmB, P, grid, smem, dp, dense);
+    default: return launch_kid<SA_KERNEL_MATERN25, CG>(st, tmA, tmB, P, grid, smem, dp, dense);
+  }
+}
+
+// the workspace is sized for the larger (2-CTA) V tile so that the launch-time choice of the CTA
+// group never changes what the caller has to provide
 int64_t workspace_bytes(int64_t b, int dp) {
-  return WS_HEADER_BYTES + ceil_div(b > 0 ? b : 1, BN) * static_cast<int64_t>(vtile_bytes(dp));
+  return WS_HEADER_BYTES + ceil_div(b > 0 ? b : 1, BN) * static_cast<int64_t>(vtile_bytes(dp, 2));
 }
 
 int launch(void* stream, int kernel, float kscale, const void* A, const float* nA, int64_t a,
@@ -676,10 +738,10 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   P.kblocks = static_cast<int>(p_pad / BK);
   P.ta = static_cast<int>(ceil_div(a, BM));
   P.tb = static_cast<int>(ceil_div(b, BN));
-  // CTA pairs that share every B tile through TMA multicast (needs at least two row tiles)
-  P.csize = (env_int("SAB_CLUSTER", 2) >= 2 && P.ta >= 2 && di.sms >= 2) ? 2 : 1;
-  const int ta_units = static_cast<int>(ceil_div(P.ta, P.csize));
-  P.nsplit = dense ? 1 : choose_nsplit(ta_units, P.tb, di.sms / P.csize, p_pad * P.csize);
+  // CTA pairs (cta_group::2): two row tiles per tcgen05.mma, each CTA stages half of every B tile
+  const int cg = (env_int("SAB_CTA_GROUP", 2) >= 2 && P.ta >= 2 && di.sms >= 2) ? 2 : 1;
+  const int ta_units = static_cast<int>(ceil_div(P.ta, cg));
+  P.nsplit = dense ? 1 : choose_nsplit(ta_units, P.tb, di.sms / cg, p_pad * cg);
   P.units = ta_units * P.nsplit;
   P.nA = nA;
   P.nB = nB;
@@ -687,6 +749,7 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   P.out = out;
   P.ldo = ldo;
   P.symmetric = symmetric;
+  P.debug = env_int("SAB_DEBUG", 0);
   {
     const float steps = static_cast<float>(P.kblocks * (BK / UMMA_K));
     const char* sv = std::getenv("SAB_SNAP");  // < 0 disables both corrections (calibration runs)
@@ -700,7 +763,8 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   else P.c0 = kscale * 2.23606797749979f;
 
   // shared memory plan: as many pipeline stages as fit, two V buffers when they fit too
-  const int vbytes = (dense ? 0 : vtile_bytes(dp)) + NB_FLOATS * 4;
+  const int stage = stage_bytes(cg);
+  const int vbytes = (dense ? 0 : vtile_bytes(dp, cg) / cg) + NB_FLOATS * 4;
   const int fixed = 32 * 4 /*vinv*/ + NUM_BARS * 8 + 64;
   int stages = env_int("SAB_STAGES", MAX_STAGES);
   int vbufs = env_int("SAB_VBUFS", 2);
@@ -708,9 +772,9 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   if (stages < 2) stages = 2;
   if (vbufs < 1) vbufs = 1;
   if (vbufs > 2) vbufs = 2;
-  if (stages * STAGE_BYTES + vbufs * vbytes + fixed > di.max_smem) vbufs = 1;
-  while (stages > 2 && stages * STAGE_BYTES + vbufs * vbytes + fixed > di.max_smem) --stages;
-  const int smem = stages * STAGE_BYTES + vbufs * vbytes + fixed;
+  while (stages > 2 && stages * stage + vbufs * vbytes + fixed > di.max_smem) --stages;
+  if (stages * stage + vbufs * vbytes + fixed > di.max_smem) vbufs = 1;
+  const int smem = stages * stage + vbufs * vbytes + fixed;
   SAB_REQUIRE(smem <= di.max_smem, "shared memory plan (%d B) exceeds the device limit (%d B)", smem,
               di.max_smem);
   P.stages = stages;
@@ -724,25 +788,21 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
     long long g = ceil_div(b, static_cast<int64_t>(rows) * 8);
     if (g > 1184) g = 1184;
     colmax_kernel<<<static_cast<int>(g), dim3(dp, rows), 0, st>>>(V, b, dp, maxbits);
-    const int np = pv_n(dp);
+    const int np = pv_n(dp, cg);
     const long long groups = static_cast<long long>(P.tb) * PV_STEPS * np * 2;
     vsplit_kernel<<<static_cast<int>(ceil_div(groups, 256)), 256, 0, st>>>(
-        V, b, dp, np, P.tb, maxbits, static_cast<uint8_t*>(ws) + WS_HEADER_BYTES);
+        V, b, dp, np, cg, P.tb, maxbits, static_cast<uint8_t*>(ws) + WS_HEADER_BYTES);
     SAB_CHECK_CUDA(cudaGetLastError());
   }
 
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap(&tmA, A, a, p_pad, lda, BM)) return rc;
-  if (int rc = make_tmap(&tmB, B, b, p_pad, ldb, BN / P.csize)) return rc;
+  if (int rc = make_tmap(&tmB, B, b, p_pad, ldb, BN / cg)) return rc;
 
-  const int clusters = P.units < di.sms / P.csize ? P.units : di.sms / P.csize;
-  const int grid = clusters * P.csize;
-  switch (kernel) {
-    case SA_KERNEL_GAUSSIAN: return launch_kid<SA_KERNEL_GAUSSIAN>(st, tmA, tmB, P, grid, smem, dp, dense);
-    case SA_KERNEL_LAPLACIAN: return launch_kid<SA_KERNEL_LAPLACIAN>(st, tmA, tmB, P, grid, smem, dp, dense);
-    case SA_KERNEL_MATERN15: return launch_kid<SA_KERNEL_MATERN15>(st, tmA, tmB, P, grid, smem, dp, dense);
-    default: return launch_kid<SA_KERNEL_MATERN25>(st, tmA, tmB, P, grid, smem, dp, dense);
-  }
+  const int groups_max = di.sms / cg;
+  const int grid = (P.units < groups_max ? P.units : groups_max) * cg;
+  if (cg == 2) return launch_cg<2>(st, kernel, tmA, tmB, P, grid, smem, dp, dense);
+  return launch_cg<1>(st, kernel, tmA, tmB, P, grid, smem, dp, dense);
 }
 
 int query_device(int* sms, int* smem) {
