@@ -91,13 +91,18 @@ int sa_kdense(void* stream, int kernel, float kscale, const void* A, const float
  * sa_potrf: in-place blocked Cholesky A = L L^T (lower).  `invdiag` receives the inverses of the
  * 128x128 diagonal blocks of L ( ceil(M/128) blocks of 128*128 floats ); they are what the
  * triangular solves use.  `info` (device int) is set to 1 + index of the first non-positive pivot,
- * or left 0.
+ * or left 0.  The trailing updates run on the tensor cores with fp16 hi/lo operand pairs staged in
+ * `workspace` (caller-owned, 256-byte aligned, at least sa_linalg_workspace_bytes(M) bytes; contents
+ * are scratch).  Elements above the 128-block diagonal are scratch as well.
  */
-int sa_potrf(void* stream, float* A, int64_t M, int64_t lda, float* invdiag, int* info);
+int64_t sa_linalg_workspace_bytes(int64_t M);
+int sa_potrf(void* stream, float* A, int64_t M, int64_t lda, float* invdiag, int* info, void* workspace,
+             int64_t workspace_bytes);
 
-/* G(lower) = alpha * L^T L + beta * I   (falkon `lauum` + `mul_triang` + add-diagonal [ext]) */
+/* G(lower) = alpha * L^T L + beta * I   (falkon `lauum` + `mul_triang` + add-diagonal [ext]);
+ * same workspace contract as sa_potrf. */
 int sa_ltl(void* stream, const float* L, int64_t M, int64_t ldl, float* G, int64_t ldg, float alpha,
-           float beta);
+           float beta, void* workspace, int64_t workspace_bytes);
 
 /* A[i, i] += value */
 int sa_add_diag(void* stream, float* A, int64_t M, int64_t lda, float value);

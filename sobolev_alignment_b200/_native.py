@@ -71,8 +71,10 @@ _SIGNATURES = {
                        c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64]),
     "sa_kdense": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                           c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int]),
-    "sa_potrf": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
-    "sa_ltl": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_float]),
+    "sa_linalg_workspace_bytes": (c_int64, [c_int64]),
+    "sa_potrf": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64]),
+    "sa_ltl": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p,
+                       c_int64]),
     "sa_add_diag": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float]),
     "sa_trsm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int]),
     "sa_coldot": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
@@ -236,20 +238,31 @@ def kdense(kernel_id: int, kscale: float, A: Prepared, B: Prepared, out: torch.T
     return out
 
 
+def _linalg_workspace(device, m: int) -> torch.Tensor:
+    """Scratch for the fp16 hi/lo operand panels of the tensor-core Cholesky updates (shared with kmv's)."""
+    nbytes = int(load().sa_linalg_workspace_bytes(m))
+    if nbytes < 0:
+        raise NativeLibraryError("bad matrix order")
+    return _workspace(device, nbytes)
+
+
 def potrf(A: torch.Tensor, invdiag: torch.Tensor, info: torch.Tensor):
     _req(A, torch.float32, "A")
     _req(invdiag, torch.float32, "invdiag")
+    ws = _linalg_workspace(A.device, A.shape[0])
     _check(load().sa_potrf(_stream(), A.data_ptr(), A.shape[0], A.stride(0), invdiag.data_ptr(),
-                           info.data_ptr()))
-    STATS.launches += 3 * (A.shape[0] // TILE) - 2
+                           info.data_ptr(), ws.data_ptr(), ws.numel()))
+    nblk = A.shape[0] // TILE
+    STATS.launches += 2 + nblk + 3 * (nblk - 1)   # scale, diagonal blocks, (panel, split, update) per step
 
 
 def ltl(L: torch.Tensor, G: torch.Tensor, alpha: float, beta: float):
     _req(L, torch.float32, "L")
     _req(G, torch.float32, "G")
+    ws = _linalg_workspace(L.device, L.shape[0])
     _check(load().sa_ltl(_stream(), L.data_ptr(), L.shape[0], L.stride(0), G.data_ptr(), G.stride(0),
-                         float(alpha), float(beta)))
-    STATS.launches += 1
+                         float(alpha), float(beta), ws.data_ptr(), ws.numel()))
+    STATS.launches += 3 + 2 * (L.shape[0] // TILE)   # scale, (split, update) per block row, diagonal
 
 
 def add_diag(A: torch.Tensor, m: int, value: float):

@@ -107,9 +107,18 @@ struct Params {
   float snap;  // squared distances below snap * (|a|^2 + |b|^2) are treated as exactly zero
   float m2g;   // -2 * (1 + accumulator-bias compensation)
   int symmetric;
+  float alpha, gamma;  // MODE_GEMM: out = gamma * out + alpha * alpha_dev[0] * A B^T
+  const float* alpha_dev;  // optional device-side factor of alpha (NULL = 1)
+  int lower;           // MODE_GEMM: only tiles that touch the lower triangle (col <= row) are computed
   int debug;   // SAB_DEBUG bit mask, timing experiments only (results are garbage): 1 = no TMA
                // loads after the first fill, 2 = epilogue skips its math, 4 = no P V products
 };
+
+// what the kernel does with S = A B^T
+enum { MODE_KMV = 0,    // out[a x dp] += k(A, B) V           (fused, K never leaves TMEM / registers)
+       MODE_DENSE = 1,  // out[a x b]   = k(A, B)
+       MODE_GEMM = 2 }; // out[a x b]   = gamma out + alpha S   (plain fp16 tensor-core GEMM, fp32 out:
+                        //                the trailing updates of the Cholesky factorisations)
 
 // k(d2) * 2^shift  (shift = 14 for the fused product so that k fills the fp16 range, 0 for dense)
 template <int KID>
@@ -137,36 +146,52 @@ __device__ __forceinline__ void column_scale(uint32_t maxbits, float* scale, flo
 template <int CG>
 struct TileIter {
   int unit, j, j0, j1;
+  // row-tile group of the current unit; lower-triangular sweeps start with the longest rows
+  __device__ __forceinline__ int group(const Params& P) const {
+    const int g = unit / P.nsplit;
+    return P.lower ? P.units / P.nsplit - 1 - g : g;
+  }
+  // column range of the current unit; units left empty by the triangle are skipped
   __device__ __forceinline__ void set_range(const Params& P) {
-    const int ch = unit % P.nsplit;
-    j0 = static_cast<int>(static_cast<long long>(ch) * P.tb / P.nsplit);
-    j1 = static_cast<int>(static_cast<long long>(ch + 1) * P.tb / P.nsplit);
+    while (unit < P.units) {
+      const int ch = unit % P.nsplit;
+      j0 = static_cast<int>(static_cast<long long>(ch) * P.tb / P.nsplit);
+      j1 = static_cast<int>(static_cast<long long>(ch + 1) * P.tb / P.nsplit);
+      if (P.lower) {  // column tiles entirely right of the unit's last row are not computed
+        const long long last_row = min(P.a, static_cast<long long>(group(P) + 1) * CG * BM) - 1;
+        j1 = min(j1, static_cast<int>(last_row / BN) + 1);
+      }
+      if (j0 < j1) break;
+      unit += static_cast<int>(gridDim.x) / CG;
+    }
     j = j0;
   }
   __device__ __forceinline__ explicit TileIter(const Params& P)
       : unit(static_cast<int>(blockIdx.x) / CG), j(0), j0(0), j1(0) {
-    if (unit < P.units) set_range(P);
+    set_range(P);
   }
   __device__ __forceinline__ bool valid(const Params& P) const { return unit < P.units; }
   __device__ __forceinline__ bool first() const { return j == j0; }
   __device__ __forceinline__ bool last() const { return j + 1 == j1; }
   // the CTAs of a pair take adjacent row tiles of the same unit (and sweep the same column tiles)
   __device__ __forceinline__ int row_tile(const Params& P, int crank) const {
-    return (unit / P.nsplit) * CG + crank;
+    return group(P) * CG + crank;
   }
   __device__ __forceinline__ void next(const Params& P) {
     if (++j == j1) {
       unit += static_cast<int>(gridDim.x) / CG;
-      if (unit < P.units) set_range(P);
+      set_range(P);
     }
   }
 };
 
-template <int KID, int DP, bool DENSE, int CG>
+template <int KID, int DP, int MODE, int CG>
 __global__ void __launch_bounds__(THREADS, 1)
 kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
            const Params P) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr bool DENSE = MODE != MODE_KMV;  // no V tile, no P V product, S drained by the epilogue
+  constexpr bool GEMM = MODE == MODE_GEMM;  // no norm tile either
   constexpr int NP = pv_n(DP, CG);          // columns of the O accumulators
   constexpr int NPC = NP / CG;              // V columns staged by this CTA
   constexpr int STAGE = stage_bytes(CG);
@@ -359,7 +384,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     }
   } else if (warp == 2) {
     // ================================ V / norm tile loader ==================================
-    if (lane == 0) {
+    if (lane == 0 && !GEMM) {
       int vb = 0;
       uint32_t vph = 0;
       for (Iter it(P); it.valid(P); it.next(P)) {
@@ -397,14 +422,70 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       const long long sym_row = P.symmetric ? grow : -1;
       const long long col0 = static_cast<long long>(it.j) * BN;
       const int cols_valid = static_cast<int>(min(static_cast<long long>(BN), P.b - col0));
-      mbar_wait(bar_vfull + 8 * vb, vph);
+      if (!GEMM) mbar_wait(bar_vfull + 8 * vb, vph);
+      if (GEMM && row_ok && P.gamma != 0.f) {
+        // the read-modify-write of C is what bounds this mode: pull this thread's 112 floats towards L2
+        // while the MMAs of the tile are still running
+        const float* cp = P.out + grow * P.ldo + col0 + cbeg;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (cbeg + 32 * q < cols_valid) prefetch_l2(cp + 32 * q);
+      }
       mbar_wait(bar_sfull + 8 * buf, (t >> 1) & 1u);
       tcgen05_fence_after();
       const float* Ns = nbuf + vb * NB_FLOATS;
       const uint32_t tacc = tmem_base + tlane + static_cast<uint32_t>(buf ? TM_S1 : TM_S0);
+      if constexpr (GEMM) {
+        // out = gamma out + alpha S.  Rows of this tile end at tile_last: column chunks right of it are
+        // above the diagonal band and left alone.  The loads of the next chunk's C values are issued
+        // before the current chunk is processed (the read-modify-write is latency bound otherwise).
+        const long long tile_last = static_cast<long long>(it.row_tile(P, crank) + 1) * BM - 1;
+        int cend = min(cbeg + HALF_COLS, cols_valid);
+        if (P.lower) cend = static_cast<int>(min(static_cast<long long>(cend), tile_last - col0 + 1));
+        const float alpha = P.alpha_dev ? P.alpha * __ldg(P.alpha_dev) : P.alpha;
+        const bool rmw = P.gamma != 0.f;
+        float* rowp = P.out + grow * P.ldo + col0;
+        float4 nv[4];
+        auto load_chunk = [&](int c0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            nv[q] = (rmw && row_ok && c0 + 16 <= cend) ? reinterpret_cast<const float4*>(rowp + c0)[q]
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        if (cbeg < cend) load_chunk(cbeg);
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+          float4 cv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cv[q] = nv[q];
+          if (c0 + 16 < cend) load_chunk(c0 + 16);
+          uint32_t r[16];
+          tmem_ld_32x16(tacc + static_cast<uint32_t>(c0), r);
+          tmem_wait_ld();
+          if (!row_ok) continue;
+          float* dst = rowp + c0;
+          if (c0 + 16 <= cend) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              cv[q].x = fmaf(alpha, __uint_as_float(r[4 * q + 0]), P.gamma * cv[q].x);
+              cv[q].y = fmaf(alpha, __uint_as_float(r[4 * q + 1]), P.gamma * cv[q].y);
+              cv[q].z = fmaf(alpha, __uint_as_float(r[4 * q + 2]), P.gamma * cv[q].z);
+              cv[q].w = fmaf(alpha, __uint_as_float(r[4 * q + 3]), P.gamma * cv[q].w);
+              reinterpret_cast<float4*>(dst)[q] = cv[q];
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+              if (c0 + c < cend) {
+                const float old = rmw ? dst[c] : 0.f;
+                dst[c] = fmaf(alpha, __uint_as_float(r[c]), P.gamma * old);
+              }
+          }
+        }
+      }
 #pragma unroll 1
       for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 16) {
-        if ((DENSE && c0 >= cols_valid) || (P.debug & 2)) break;
+        if ((DENSE && c0 >= cols_valid) || (P.debug & 2) || GEMM) break;
         uint32_t r[16];
         tmem_ld_32x16(tacc + static_cast<uint32_t>(c0), r);
         tmem_wait_ld();
@@ -450,7 +531,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       if (lane == 0) {
         if (CG == 1) mbar_arrive(bar_pready + 8 * buf);
         else mbar_arrive_cluster(lead_pready + 8 * buf);
-        mbar_arrive(bar_vempty + 8 * vb);
+        if (!GEMM) mbar_arrive(bar_vempty + 8 * vb);
       }
       if (!DENSE && it.last()) {
         if (half == 0) {
@@ -640,10 +721,10 @@ static int choose_nsplit(int ta, int tb, int sms, long long p_pad) {
   return best_ns;
 }
 
-template <int KID, int DP, bool DENSE, int CG>
+template <int KID, int DP, int MODE, int CG>
 static int launch_inst(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB,
                        const Params& P, int grid, int smem) {
-  auto kern = kmv_kernel<KID, DP, DENSE, CG>;
+  auto kern = kmv_kernel<KID, DP, MODE, CG>;
   SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   if (CG == 1) {
     kern<<<grid, THREADS, smem, st>>>(tmA, tmB, P);
@@ -668,17 +749,17 @@ static int launch_inst(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMa
 
 template <int KID, int CG>
 static int launch_kid(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                      const Params& P, int grid, int smem, int dp, bool dense) {
-  if (dense) return launch_inst<KID, 4, true, CG>(st, tmA, tmB, P, grid, smem);
+                      const Params& P, int grid, int smem, int dp, int mode) {
+  if (mode == MODE_DENSE) return launch_inst<KID, 4, MODE_DENSE, CG>(st, tmA, tmB, P, grid, smem);
   switch (dp) {
-    case 4: return launch_inst<KID, 4, false, CG>(st, tmA, tmB, P, grid, smem);
-    case 8: return launch_inst<KID, 8, false, CG>(st, tmA, tmB, P, grid, smem);
-    case 12: return launch_inst<KID, 12, false, CG>(st, tmA, tmB, P, grid, smem);
-    case 16: return launch_inst<KID, 16, false, CG>(st, tmA, tmB, P, grid, smem);
-    case 20: return launch_inst<KID, 20, false, CG>(st, tmA, tmB, P, grid, smem);
-    case 24: return launch_inst<KID, 24, false, CG>(st, tmA, tmB, P, grid, smem);
-    case 28: return launch_inst<KID, 28, false, CG>(st, tmA, tmB, P, grid, smem);
-    case 32: return launch_inst<KID, 32, false, CG>(st, tmA, tmB, P, grid, smem);
+    case 4: return launch_inst<KID, 4, MODE_KMV, CG>(st, tmA, tmB, P, grid, smem);
+    case 8: return launch_inst<KID, 8, MODE_KMV, CG>(st, tmA, tmB, P, grid, smem);
+    case 12: return launch_inst<KID, 12, MODE_KMV, CG>(st, tmA, tmB, P, grid, smem);
+    case 16: return launch_inst<KID, 16, MODE_KMV, CG>(st, tmA, tmB, P, grid, smem);
+    case 20: return launch_inst<KID, 20, MODE_KMV, CG>(st, tmA, tmB, P, grid, smem);
+    case 24: return launch_inst<KID, 24, MODE_KMV, CG>(st, tmA, tmB, P, grid, smem);
+    case 28: return launch_inst<KID, 28, MODE_KMV, CG>(st, tmA, tmB, P, grid, smem);
+    case 32: return launch_inst<KID, 32, MODE_KMV, CG>(st, tmA, tmB, P, grid, smem);
   }
   set_error("dp must be a multiple of 4 in [4, 32], got %d", dp);
   return 2;
@@ -686,12 +767,13 @@ static int launch_kid(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap
 
 template <int CG>
 static int launch_cg(cudaStream_t st, int kernel, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                     const Params& P, int grid, int smem, int dp, bool dense) {
+                     const Params& P, int grid, int smem, int dp, int mode) {
+  if (mode == MODE_GEMM) return launch_inst<SA_KERNEL_GAUSSIAN, 4, MODE_GEMM, CG>(st, tmA, tmB, P, grid, smem);
   switch (kernel) {
-    case SA_KERNEL_GAUSSIAN: return launch_kid<SA_KERNEL_GAUSSIAN, CG>(st, tmA, tmB, P, grid, smem, dp, dense);
-    case SA_KERNEL_LAPLACIAN: return launch_kid<SA_KERNEL_LAPLACIAN, CG>(st, tmA, tmB, P, grid, smem, dp, dense);
-    case SA_KERNEL_MATERN15: return launch_kid<SA_KERNEL_MATERN15, CG>(st, tmA, tmB, P, grid, smem, dp, dense);
-    default: return launch_kid<SA_KERNEL_MATERN25, CG>(st, tmA, tmB, P, grid, smem, dp, dense);
+    case SA_KERNEL_GAUSSIAN: return launch_kid<SA_KERNEL_GAUSSIAN, CG>(st, tmA, tmB, P, grid, smem, dp, mode);
+    case SA_KERNEL_LAPLACIAN: return launch_kid<SA_KERNEL_LAPLACIAN, CG>(st, tmA, tmB, P, grid, smem, dp, mode);
+    case SA_KERNEL_MATERN15: return launch_kid<SA_KERNEL_MATERN15, CG>(st, tmA, tmB, P, grid, smem, dp, mode);
+    default: return launch_kid<SA_KERNEL_MATERN25, CG>(st, tmA, tmB, P, grid, smem, dp, mode);
   }
 }
 
@@ -703,8 +785,9 @@ int64_t workspace_bytes(int64_t b, int dp) {
 
 int launch(void* stream, int kernel, float kscale, const void* A, const float* nA, int64_t a,
            int64_t lda, const void* B, const float* nB, int64_t b, int64_t ldb, int64_t p_pad,
-           const float* V, int dp, float* out, int64_t ldo, int symmetric, bool dense, void* ws,
-           int64_t ws_bytes) {
+           const float* V, int dp, float* out, int64_t ldo, int symmetric, int mode, void* ws,
+           int64_t ws_bytes, float alpha, float gamma, int lower, const float* alpha_dev) {
+  const bool dense = mode != MODE_KMV;
   SAB_REQUIRE(kernel >= 0 && kernel <= 3, "unknown kernel id %d", kernel);
   SAB_REQUIRE(a >= 0 && b >= 0, "negative row count");
   if (a == 0 || b == 0) return 0;
@@ -716,6 +799,7 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   SAB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(nB) & 15) == 0,
               "operands must be 16-byte aligned");
+  SAB_REQUIRE(mode != MODE_GEMM || (ldo % 4 == 0), "GEMM output row stride must be a multiple of 4");
   SAB_REQUIRE(a < (1ll << 31) && b < (1ll << 31), "row counts must fit in int32");
   if (!dense) {
     SAB_REQUIRE(V != nullptr && out != nullptr, "V / out must not be NULL");
@@ -741,7 +825,8 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   // CTA pairs (cta_group::2): two row tiles per tcgen05.mma, each CTA stages half of every B tile
   const int cg = (env_int("SAB_CTA_GROUP", 2) >= 2 && P.ta >= 2 && di.sms >= 2) ? 2 : 1;
   const int ta_units = static_cast<int>(ceil_div(P.ta, cg));
-  P.nsplit = dense ? 1 : choose_nsplit(ta_units, P.tb, di.sms / cg, p_pad * cg);
+  if (mode == MODE_GEMM) P.nsplit = static_cast<int>(ceil_div(P.tb, env_int("SAB_GEMM_CHUNK", 8)));  // no reduction across column tiles: short units balance the triangle
+  else P.nsplit = dense ? 1 : choose_nsplit(ta_units, P.tb, di.sms / cg, p_pad * cg);
   P.units = ta_units * P.nsplit;
   P.nA = nA;
   P.nB = nB;
@@ -749,6 +834,10 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   P.out = out;
   P.ldo = ldo;
   P.symmetric = symmetric;
+  P.alpha = alpha;
+  P.alpha_dev = alpha_dev;
+  P.gamma = gamma;
+  P.lower = lower;
   P.debug = env_int("SAB_DEBUG", 0);
   {
     const float steps = static_cast<float>(P.kblocks * (BK / UMMA_K));
@@ -801,8 +890,8 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
 
   const int groups_max = di.sms / cg;
   const int grid = (P.units < groups_max ? P.units : groups_max) * cg;
-  if (cg == 2) return launch_cg<2>(st, kernel, tmA, tmB, P, grid, smem, dp, dense);
-  return launch_cg<1>(st, kernel, tmA, tmB, P, grid, smem, dp, dense);
+  if (cg == 2) return launch_cg<2>(st, kernel, tmA, tmB, P, grid, smem, dp, mode);
+  return launch_cg<1>(st, kernel, tmA, tmB, P, grid, smem, dp, mode);
 }
 
 int query_device(int* sms, int* smem) {
@@ -826,15 +915,27 @@ extern "C" int sa_kmv(void* stream, int kernel, float kscale, const void* A, con
                       int64_t p_pad, const float* V, int dp, float* out, int symmetric, void* workspace,
                       int64_t workspace_bytes) {
   return sab::kmv::launch(stream, kernel, kscale, A, nA, a, lda, B, nB, b, ldb, p_pad, V, dp, out, dp,
-                          symmetric, false, workspace, workspace_bytes);
+                          symmetric, sab::kmv::MODE_KMV, workspace, workspace_bytes, 0.f, 0.f, 0, nullptr);
 }
 
 extern "C" int sa_kdense(void* stream, int kernel, float kscale, const void* A, const float* nA,
                          int64_t a, int64_t lda, const void* B, const float* nB, int64_t b,
                          int64_t ldb, int64_t p_pad, float* out, int64_t ldo, int symmetric) {
   return sab::kmv::launch(stream, kernel, kscale, A, nA, a, lda, B, nB, b, ldb, p_pad, nullptr, 4, out,
-                          ldo, symmetric, true, nullptr, 0);
+                          ldo, symmetric, sab::kmv::MODE_DENSE, nullptr, 0, 0.f, 0.f, 0, nullptr);
 }
+
+namespace sab {
+// out[ra x rb] = gamma * out + alpha * alpha_dev[0] * A B^T on the fp16 tensor path (fp32 accumulate /
+// output).  A [ra x k], B [rb x k]: fp16 row-major, k a multiple of 64.  lower != 0: only tiles that
+// touch col <= row are computed (everything right of a row tile's last row is left untouched).
+// alpha_dev: optional device-side factor (the power-of-two operand scaling lives on the device).
+int tc_gemm_nt(void* stream, const void* A, int64_t ra, int64_t lda, const void* B, int64_t rb, int64_t ldb,
+               int64_t k, float* out, int64_t ldo, float alpha, const float* alpha_dev, float gamma, int lower) {
+  return kmv::launch(stream, SA_KERNEL_GAUSSIAN, 0.f, A, nullptr, ra, lda, B, nullptr, rb, ldb, k, nullptr, 4,
+                     out, ldo, 0, kmv::MODE_GEMM, nullptr, 0, alpha, gamma, lower, alpha_dev);
+}
+}  // namespace sab
 
 extern "C" int sa_device_info(int* sm_count, int* smem_bytes) {
   return sab::kmv::query_device(sm_count, smem_bytes);

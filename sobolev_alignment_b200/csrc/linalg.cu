@@ -4,8 +4,12 @@
 // identity block, which leaves the Cholesky factors and every solve unchanged), row-major, lower
 // triangle significant:
 //   sa_potrf   blocked right-looking Cholesky: 128x128 diagonal factor+inverse in shared memory,
-//              panel = A * inv(L_kk)^T, trailing update = register-tiled SIMT SGEMM (NT)
-//   sa_ltl     G = alpha L^T L + beta I on the lower tiles (TN SGEMM over the rows below the tile)
+//              panel = A * inv(L_kk)^T (SIMT SGEMM), trailing update C -= P P^T on the tcgen05 tensor
+//              path: the fp32 panel is split into fp16 pairs x 2^s = hi + lo and multiplied as the
+//              K-concatenated product [lo|hi|hi] [hi|lo|hi]^T (lo lo dropped, ~2^-22 relative) by the
+//              GEMM mode of the fused kernel (kmv.cu), which keeps the update HBM-bound
+//   sa_ltl     G = alpha L^T L + beta I as rank-128 updates with the block rows of L (same split,
+//              transposed), also on the tensor path
 //   sa_trsm    block forward / backward substitution; one launch per 128-row block step, each CTA
 //              streams one 128x128 tile of L (coalesced 128-bit loads) against the M x dp rhs
 //   sa_coldot / sa_cg_update / sa_cg_direction / sa_axpby   CG vector kernels, coalesced over the
@@ -14,10 +18,16 @@
 // Replaces falkon `FalkonPreconditioner` (potrf, lauum, mul_triang, trsm) and
 // `ConjugateGradient.solve` [external dependency], reached from
 // /root/reference/sobolev_alignment/krr_approx.py:227.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
 #include "../../include/sobolev_b200.h"
 #include "common.cuh"
 
 namespace sab {
+int tc_gemm_nt(void* stream, const void* A, int64_t ra, int64_t lda, const void* B, int64_t rb, int64_t ldb,
+               int64_t k, float* out, int64_t ldo, float alpha, const float* alpha_dev, float gamma, int lower);
 namespace la {
 
 constexpr int TS = 128;        // tile size
@@ -152,8 +162,17 @@ sgemm_kernel(float* __restrict__ A, long long lda, const float* __restrict__ aux
             make_float4(acc[i][jh * 4], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
     }
   } else if (MODE == MODE_SYRK) {
+    // jlim = number of block columns right of k that are updated (all of them for the classic
+    // right-looking step, the rest of the current outer panel for the two-level factorisation)
+    const int jlim = static_cast<int>(alpha);
     int ti, tj;
-    tri_index(blockIdx.x, ti, tj);
+    if (jlim >= nblk - k - 1) {
+      tri_index(blockIdx.x, ti, tj);
+    } else {
+      ti = static_cast<int>(blockIdx.x) / jlim;
+      tj = static_cast<int>(blockIdx.x) % jlim;
+      if (tj > ti) return;
+    }
     const long long bi = k + 1 + ti, bj = k + 1 + tj;
     const float* Li = A + bi * TS * lda + static_cast<long long>(k) * TS;
     const float* Lj = A + bj * TS * lda + static_cast<long long>(k) * TS;
@@ -203,7 +222,10 @@ sgemm_kernel(float* __restrict__ A, long long lda, const float* __restrict__ aux
 }
 
 // --------------------------------------------------------------------------------------------
-// 128x128 diagonal block: Cholesky in shared memory, then the explicit inverse of the factor.
+// 128x128 diagonal block: Cholesky, then the explicit inverse of the factor, both register resident.
+// 256 threads as a 16 x 16 grid; thread (ty, tx) owns the elements (ty + 16 a, tx + 16 b), a, b < 8
+// (cyclic, so the shrinking active region stays balanced).  Every elimination step broadcasts one
+// column (and, for the inverse, one row) through shared memory and is a rank-1 update of 64 registers.
 // --------------------------------------------------------------------------------------------
 constexpr int LDD = TS + 1;
 
@@ -211,10 +233,12 @@ __global__ void __launch_bounds__(256)
 diag_factor_kernel(float* __restrict__ A, long long lda, int k, float* __restrict__ invdiag,
                    int* __restrict__ info) {
   extern __shared__ float dsm[];
-  float* Ls = dsm;                 // [128][129]
-  float* Xs = dsm + TS * LDD;      // [128][129]
+  float* Ls = dsm;                      // [128][129] staging of the block / of L
+  float* colb = dsm + TS * LDD;         // [2][128] column broadcast (double buffered)
+  float* rowb = colb + 2 * TS;          // [2][128] row broadcast
   float* blk = A + static_cast<long long>(k) * TS * lda + static_cast<long long>(k) * TS;
   const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
   for (int idx = tid; idx < TS * TS / 4; idx += 256) {
     const int r = idx >> 5, cq = idx & 31;
     const float4 v = *reinterpret_cast<const float4*>(blk + static_cast<long long>(r) * lda + cq * 4);
@@ -224,46 +248,102 @@ diag_factor_kernel(float* __restrict__ A, long long lda, int k, float* __restric
     Ls[r * LDD + cq * 4 + 3] = v.w;
   }
   __syncthreads();
-  // right-looking Cholesky on the lower triangle
+  float a[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[i][j] = Ls[(ty + 16 * i) * LDD + tx + 16 * j];
+
+  // ---- right-looking Cholesky: after step j, column j of `a` holds L[:, j]
   for (int j = 0; j < TS; ++j) {
-    const float piv = Ls[j * LDD + j];
+    float* cb = colb + (j & 1) * TS;
+    const int jb = j >> 4, jx = j & 15;
+    if (tx == jx) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+          if (b == jb) cb[ty + 16 * i] = a[i][b];
+    }
+    __syncthreads();
+    const float piv = cb[j];
     if (tid == 0 && !(piv > 0.f)) atomicCAS(info, 0, k * TS + j + 1);
     const float d = sqrtf(fmaxf(piv, 1e-30f));
     const float inv = 1.f / d;
-    __syncthreads();
-    for (int i = j + tid; i < TS; i += 256) Ls[i * LDD + j] = (i == j) ? d : Ls[i * LDD + j] * inv;
-    __syncthreads();
-    // trailing: A[i][c] -= L[i][j] L[c][j] for j < c <= i
-    const int rem = TS - 1 - j;
-    for (int e = tid; e < rem * rem; e += 256) {
-      const int i = j + 1 + e / rem, c = j + 1 + e % rem;
-      if (c <= i) Ls[i * LDD + c] = fmaf(-Ls[i * LDD + j], Ls[c * LDD + j], Ls[i * LDD + c]);
-    }
-    __syncthreads();
-  }
-  // inverse: column c of X = L^-1 by forward substitution, one thread per column
-  if (tid < TS) {
-    const int c = tid;
-    for (int i = 0; i < c; ++i) Xs[i * LDD + c] = 0.f;
-    Xs[c * LDD + c] = 1.f / Ls[c * LDD + c];
-    for (int i = c + 1; i < TS; ++i) {
-      float s0 = 0.f, s1 = 0.f;
-      int kk = c;
-      for (; kk + 1 < i; kk += 2) {
-        s0 = fmaf(Ls[i * LDD + kk], Xs[kk * LDD + c], s0);
-        s1 = fmaf(Ls[i * LDD + kk + 1], Xs[(kk + 1) * LDD + c], s1);
-      }
-      if (kk < i) s0 = fmaf(Ls[i * LDD + kk], Xs[kk * LDD + c], s0);
-      Xs[i * LDD + c] = -(s0 + s1) / Ls[i * LDD + i];
+    float li[8], lc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) li[i] = (ty + 16 * i > j) ? cb[ty + 16 * i] * inv : 0.f;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) lc[b] = (tx + 16 * b > j) ? cb[tx + 16 * b] * inv : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) a[i][b] = fmaf(-li[i], lc[b], a[i][b]);
+    if (tx == jx) {  // column j itself becomes L[:, j]
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+          if (b == jb) {
+            const int r = ty + 16 * i;
+            a[i][b] = r > j ? li[i] : (r == j ? d : a[i][b]);
+          }
     }
   }
   __syncthreads();
-  float* inv_out = invdiag + static_cast<long long>(k) * TS * TS;
+  // L (lower, zero above the diagonal) back to shared memory
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int r = ty + 16 * i, c = tx + 16 * b;
+      Ls[r * LDD + c] = c <= r ? a[i][b] : 0.f;
+    }
+  __syncthreads();
   for (int idx = tid; idx < TS * TS; idx += 256) {
     const int r = idx >> 7, c = idx & 127;
-    blk[static_cast<long long>(r) * lda + c] = (c <= r) ? Ls[r * LDD + c] : 0.f;
-    inv_out[idx] = Xs[r * LDD + c];
+    blk[static_cast<long long>(r) * lda + c] = Ls[r * LDD + c];
   }
+
+  // ---- X = L^-1 by forward elimination on the identity: after step j row j of X is final and
+  // X[i, :] -= L[i, j] X[j, :] for i > j.  `a` is reused for X.
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) a[i][b] = (ty + 16 * i == tx + 16 * b) ? 1.f : 0.f;
+  for (int j = 0; j < TS; ++j) {
+    float* rb = rowb + (j & 1) * TS;
+    const int jb = j >> 4, jy = j & 15;
+    const float dinv = 1.f / Ls[j * LDD + j];
+    if (ty == jy) {  // finish row j and broadcast it
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+          if (i == jb) {
+            a[i][b] *= dinv;
+            rb[tx + 16 * b] = a[i][b];
+          }
+    }
+    __syncthreads();
+    float li[8], xr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) li[i] = (ty + 16 * i > j) ? Ls[(ty + 16 * i) * LDD + j] : 0.f;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) xr[b] = rb[tx + 16 * b];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) a[i][b] = fmaf(-li[i], xr[b], a[i][b]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) Ls[(ty + 16 * i) * LDD + tx + 16 * b] = a[i][b];
+  __syncthreads();
+  float* inv_out = invdiag + static_cast<long long>(k) * TS * TS;
+  for (int idx = tid; idx < TS * TS; idx += 256) inv_out[idx] = Ls[(idx >> 7) * LDD + (idx & 127)];
 }
 
 // --------------------------------------------------------------------------------------------
@@ -463,6 +543,147 @@ trsm_step_kernel(const float* __restrict__ L, long long ldl, const float* __rest
 }
 
 // --------------------------------------------------------------------------------------------
+// fp32 -> fp16 hi/lo operands of the tensor-core updates
+// --------------------------------------------------------------------------------------------
+constexpr int HDR_FLOATS = 64;  // workspace header: [0] max bits, [1] operand scale 2^s, [2] 2^-2s
+
+__global__ void absmax_kernel(const float* __restrict__ A, long long M, long long lda, int diag_only,
+                              unsigned* __restrict__ maxbits) {
+  float m = 0.f;
+  if (diag_only) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < M;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+      m = fmaxf(m, fabsf(A[i * lda + i]));
+  } else {  // lower triangle incl. diagonal, one row per block iteration
+    for (long long r = blockIdx.x; r < M; r += gridDim.x)
+      for (long long c = threadIdx.x; c <= r; c += blockDim.x) m = fmaxf(m, fabsf(A[r * lda + c]));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(maxbits, __float_as_uint(m));
+}
+
+// scale = power of two that brings the largest operand entry into [2^12, 2^13): hi = fp16(x scale) is
+// far from overflow and lo = fp16(x scale - hi) stays a NORMAL fp16 for every |x| > 2^-26 max.
+// take_sqrt: the entries are bounded by sqrt(max) (Cholesky factor of a matrix with that diagonal).
+__global__ void make_scale_kernel(float* hdr, int take_sqrt) {
+  float m = __uint_as_float(reinterpret_cast<unsigned*>(hdr)[0]);
+  if (take_sqrt) m = sqrtf(m);
+  int e = 0;
+  if (m > 0.f && isfinite(m)) frexpf(m, &e);  // m = f 2^e, f in [0.5, 1)
+  const float sc = ldexpf(1.f, 13 - e);
+  hdr[1] = sc;
+  hdr[2] = 1.f / (sc * sc);
+}
+
+// fp32 operand -> K-concatenated fp16 pairs, W = K extent of the fp32 operand (multiple of 64):
+//   outA[r] = [ lo | hi | hi ],  outB[r] = [ hi | lo | hi ]   (row stride 3 W), x 2^s = hi + lo
+// so that outA outB^T = lo hi + hi lo + hi hi.  The small terms come first: the truncating tensor-core
+// accumulator then only sees W/16 steps at full magnitude.  One thread per 8 consecutive K elements.
+// transpose = 0: operand row r, K index k  <-  src[r][k]   (the Cholesky panel).
+// transpose = 1: operand row r, K index k  <-  src[k][r] masked to r <= k_g0 + k   (block row of L
+//                used as L^T; k_g0 = global row of src[0]).
+__global__ void split_f16_kernel(const float* __restrict__ src, long long ld, long long rows, int W, int transpose,
+                                 long long k_g0, const float* __restrict__ hdr, __half* __restrict__ outA,
+                                 __half* __restrict__ outB) {
+  const float sc = hdr[1];
+  const int kgroups = W / 8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  long long r;
+  int kg;
+  if (transpose) {  // consecutive threads -> consecutive operand rows (= consecutive src columns)
+    kg = static_cast<int>(gid / rows);
+    r = gid % rows;
+    if (kg >= kgroups) return;
+  } else {
+    r = gid / kgroups;
+    kg = static_cast<int>(gid % kgroups);
+    if (r >= rows) return;
+  }
+  float x[8];
+  if (transpose) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long k = kg * 8 + i;
+      x[i] = (r <= k_g0 + k) ? src[k * ld + r] : 0.f;  // L[k_g0 + k][r], lower triangle only
+    }
+  } else {
+    const float4 v0 = *reinterpret_cast<const float4*>(src + r * ld + kg * 8);
+    const float4 v1 = *reinterpret_cast<const float4*>(src + r * ld + kg * 8 + 4);
+    x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+    x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+  }
+  __align__(16) __half hi[8];
+  __align__(16) __half lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float v = x[i] * sc;
+    hi[i] = __float2half_rn(v);
+    lo[i] = __float2half_rn(v - __half2float(hi[i]));
+  }
+  const uint4 H = *reinterpret_cast<const uint4*>(hi), L = *reinterpret_cast<const uint4*>(lo);
+  __half* a = outA + r * (3ll * W) + kg * 8;
+  __half* b = outB + r * (3ll * W) + kg * 8;
+  *reinterpret_cast<uint4*>(a) = L;
+  *reinterpret_cast<uint4*>(a + W) = H;
+  *reinterpret_cast<uint4*>(a + 2 * W) = H;
+  *reinterpret_cast<uint4*>(b) = H;
+  *reinterpret_cast<uint4*>(b + W) = L;
+  *reinterpret_cast<uint4*>(b + 2 * W) = H;
+}
+
+// The diagonal of a tensor-core update is a sum of squares, where the truncating accumulator is
+// biased; it decides positive definiteness, so it is computed here in fp32 and written back over the
+// tensor-core result afterwards.
+//   d[i] = C[i][i] + coef * sum_k P[i][k]^2      P = panel rows, W columns; one warp per row
+__global__ void exact_diag_kernel(const float* __restrict__ C, long long ldc, const float* __restrict__ src,
+                                  long long ld, long long rows, int W, float coef, float* __restrict__ dsave) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= rows) return;
+  float s = 0.f;
+  for (int k = lane; k < W; k += 32) {
+    const float v = src[i * ld + k];
+    s = fmaf(v, v, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) dsave[i] = fmaf(coef, s, C[i * ldc + i]);
+}
+//   d[i] = gamma * G[i][i] + coef * sum_k L[k][i]^2 over the W slab rows with k_g0 + k >= i; one
+//   thread per column i (consecutive threads read consecutive floats of a row)
+__global__ void exact_diag_t_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ src,
+                                    long long ld, long long cols, int W, long long k_g0, float gamma, float coef,
+                                    float* __restrict__ dsave) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= cols) return;
+  float s0 = 0.f, s1 = 0.f;
+  long long kfirst = i - k_g0;
+  if (kfirst < 0) kfirst = 0;
+  int k = static_cast<int>(kfirst);
+  for (; k + 1 < W; k += 2) {
+    const float v0 = src[static_cast<long long>(k) * ld + i];
+    const float v1 = src[static_cast<long long>(k + 1) * ld + i];
+    s0 = fmaf(v0, v0, s0);
+    s1 = fmaf(v1, v1, s1);
+  }
+  if (k < W) {
+    const float v0 = src[static_cast<long long>(k) * ld + i];
+    s0 = fmaf(v0, v0, s0);
+  }
+  const float old = gamma != 0.f ? gamma * G[i * ldg + i] : 0.f;
+  dsave[i] = fmaf(coef, s0 + s1, old);
+}
+
+__global__ void restore_diag_kernel(float* __restrict__ C, long long ldc, long long rows,
+                                    const float* __restrict__ dsave) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < rows) C[i * ldc + i] = dsave[i];
+}
+
+// the tensor-core accumulator truncates: an all-positive sum over W/16 steps at growing magnitude comes
+// out low by ~0.8e-7 per step (calibrated in kmv.cu); the update is rescaled by the matching gain
+static inline float tc_gain(int W) { return 1.f + 0.8e-7f * static_cast<float>(W / 16); }
+
+// --------------------------------------------------------------------------------------------
 // small elementwise / reduction kernels
 // --------------------------------------------------------------------------------------------
 __global__ void add_diag_kernel(float* A, long long M, long long lda, float v) {
@@ -588,21 +809,101 @@ using namespace sab::la;
               "storage (M=%lld ld=%lld)",                                                             \
               (long long)(M), (long long)(ld))
 
-extern "C" int sa_potrf(void* stream, float* A, int64_t M, int64_t lda, float* invdiag, int* info) {
+static bool use_tensor_path() {
+  const char* v = std::getenv("SAB_LINALG_SIMT");
+  return !(v && std::atoi(v) != 0);
+}
+
+// width (in 128-blocks) of the outer panels of the two-level factorisation: the trailing matrix is
+// read and written once per outer panel, so wider panels move the update from HBM-bound to tensor-bound
+static int outer_blocks() {
+  const char* v = std::getenv("SAB_CHOL_NB");
+  int nb = v ? std::atoi(v) : 512;
+  if (nb < TS) nb = TS;
+  if (nb > 1024) nb = 1024;
+  return nb / TS;
+}
+
+extern "C" int64_t sa_linalg_workspace_bytes(int64_t M) {
+  if (M <= 0) return -1;
+  const int64_t W = static_cast<int64_t>(outer_blocks()) * TS;
+  return HDR_FLOATS * 4 + M * 4 + 2 * M * 3 * W * 2 + 256;
+}
+
+#define SAB_REQUIRE_WS(M, ws, bytes)                                                                  \
+  SAB_REQUIRE((ws) != nullptr && (reinterpret_cast<uintptr_t>(ws) & 255) == 0 &&                      \
+                  (bytes) >= sa_linalg_workspace_bytes(M),                                            \
+              "workspace must be 256-byte aligned and hold sa_linalg_workspace_bytes(M) = %lld bytes", \
+              (long long)sa_linalg_workspace_bytes(M))
+
+struct LinalgWs {
+  float* hdr;
+  float* dsave;
+  __half* opA;
+  __half* opB;
+};
+static LinalgWs carve(void* workspace, int64_t M) {
+  LinalgWs w;
+  w.hdr = static_cast<float*>(workspace);
+  w.dsave = w.hdr + HDR_FLOATS;
+  uintptr_t p = reinterpret_cast<uintptr_t>(w.dsave + M);
+  p = (p + 255) & ~static_cast<uintptr_t>(255);
+  w.opA = reinterpret_cast<__half*>(p);
+  w.opB = w.opA + M * 3 * static_cast<int64_t>(outer_blocks()) * TS;
+  return w;
+}
+
+extern "C" int sa_potrf(void* stream, float* A, int64_t M, int64_t lda, float* invdiag, int* info,
+                        void* workspace, int64_t workspace_bytes) {
   SAB_REQUIRE_MAT(M, lda, A);
   SAB_REQUIRE(invdiag != nullptr && info != nullptr, "invdiag / info must not be NULL");
+  SAB_REQUIRE_WS(M, workspace, workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nblk = static_cast<int>(M / TS);
-  const int dsmem = 2 * TS * LDD * static_cast<int>(sizeof(float));
+  const int dsmem = (TS * LDD + 4 * TS) * static_cast<int>(sizeof(float));
   SAB_CHECK_CUDA(cudaFuncSetAttribute(diag_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dsmem));
   SAB_CHECK_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
-  for (int k = 0; k < nblk; ++k) {
-    diag_factor_kernel<<<1, 256, dsmem, st>>>(A, lda, k, invdiag, info);
-    const int rem = nblk - k - 1;
-    if (rem > 0) {
-      sgemm_kernel<MODE_PANEL><<<rem, 256, 0, st>>>(A, lda, invdiag + static_cast<long long>(k) * TS * TS,
-                                                    TS, k, nblk, 0.f, 0.f);
-      sgemm_kernel<MODE_SYRK><<<rem * (rem + 1) / 2, 256, 0, st>>>(A, lda, nullptr, 0, k, nblk, 0.f, 0.f);
+  const bool tensor = use_tensor_path();
+  const int nbb = tensor ? outer_blocks() : nblk;  // SIMT: classic right-looking (one "outer panel")
+  const LinalgWs w = carve(workspace, M);
+  if (tensor) {
+    // |L_ij| <= sqrt(max_i A_ii): one power-of-two operand scale for the whole factorisation
+    SAB_CHECK_CUDA(cudaMemsetAsync(w.hdr, 0, HDR_FLOATS * 4, st));
+    absmax_kernel<<<static_cast<int>(ceil_div(M, 256)), 256, 0, st>>>(A, M, lda, 1,
+                                                                      reinterpret_cast<unsigned*>(w.hdr));
+    make_scale_kernel<<<1, 1, 0, st>>>(w.hdr, 1);
+  }
+  for (int k0 = 0; k0 < nblk; k0 += nbb) {
+    const int kend = k0 + nbb < nblk ? k0 + nbb : nblk;
+    // ---- factor the outer panel (columns [k0, kend) x all rows below) with 128-wide fp32 SIMT steps
+    for (int k = k0; k < kend; ++k) {
+      diag_factor_kernel<<<1, 256, dsmem, st>>>(A, lda, k, invdiag, info);
+      const int rem = nblk - k - 1;
+      if (rem == 0) break;
+      sgemm_kernel<MODE_PANEL><<<rem, 256, 0, st>>>(A, lda, invdiag + static_cast<long long>(k) * TS * TS, TS, k,
+                                                    nblk, 0.f, 0.f);
+      const int jlim = (tensor ? kend : nblk) - k - 1;  // block columns right of k still inside the panel
+      if (jlim >= rem)
+        sgemm_kernel<MODE_SYRK><<<rem * (rem + 1) / 2, 256, 0, st>>>(A, lda, nullptr, 0, k, nblk,
+                                                                     static_cast<float>(jlim), 0.f);
+      else if (jlim > 0)
+        sgemm_kernel<MODE_SYRK><<<rem * jlim, 256, 0, st>>>(A, lda, nullptr, 0, k, nblk, static_cast<float>(jlim), 0.f);
+    }
+    // ---- trailing update C -= P P^T on the tensor cores, P = the finished panel below row kend*128
+    if (tensor && kend < nblk) {
+      const long long rows = static_cast<long long>(nblk - kend) * TS;
+      const int W = (kend - k0) * TS;
+      float* panel = A + static_cast<long long>(kend) * TS * lda + static_cast<long long>(k0) * TS;
+      float* C = A + static_cast<long long>(kend) * TS * (lda + 1);
+      exact_diag_kernel<<<static_cast<int>(ceil_div(rows * 32, 256)), 256, 0, st>>>(C, lda, panel, lda, rows, W, -1.f,
+                                                                                w.dsave);
+      split_f16_kernel<<<static_cast<int>(ceil_div(rows * (W / 8), 256)), 256, 0, st>>>(panel, lda, rows, W, 0, 0, w.hdr,
+                                                                                     w.opA, w.opB);
+      SAB_CHECK_CUDA(cudaGetLastError());
+      if (int rc = tc_gemm_nt(stream, w.opA, rows, 3 * W, w.opB, rows, 3 * W, 3 * W, C, lda, -tc_gain(W), w.hdr + 2,
+                              1.f, 1))
+        return rc;
+      restore_diag_kernel<<<static_cast<int>(ceil_div(rows, 256)), 256, 0, st>>>(C, lda, rows, w.dsave);
     }
   }
   SAB_CHECK_CUDA(cudaGetLastError());
@@ -610,14 +911,44 @@ extern "C" int sa_potrf(void* stream, float* A, int64_t M, int64_t lda, float* i
 }
 
 extern "C" int sa_ltl(void* stream, const float* L, int64_t M, int64_t ldl, float* G, int64_t ldg,
-                      float alpha, float beta) {
+                      float alpha, float beta, void* workspace, int64_t workspace_bytes) {
   SAB_REQUIRE_MAT(M, ldl, L);
   SAB_REQUIRE_MAT(M, ldg, G);
   SAB_REQUIRE(L != G, "sa_ltl is out of place");
+  SAB_REQUIRE_WS(M, workspace, workspace_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nblk = static_cast<int>(M / TS);
   SAB_REQUIRE(nblk <= 2048, "matrix order %lld too large", (long long)M);
-  sgemm_kernel<MODE_LTL><<<nblk * (nblk + 1) / 2, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      G, ldg, L, ldl, 0, nblk, alpha, beta);
+  if (!use_tensor_path()) {
+    sgemm_kernel<MODE_LTL><<<nblk * (nblk + 1) / 2, 256, 0, st>>>(G, ldg, L, ldl, 0, nblk, alpha, beta);
+    SAB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  const LinalgWs w = carve(workspace, M);
+  const int nbb = outer_blocks();
+  SAB_CHECK_CUDA(cudaMemsetAsync(w.hdr, 0, HDR_FLOATS * 4, st));
+  absmax_kernel<<<1184, 256, 0, st>>>(L, M, ldl, 0, reinterpret_cast<unsigned*>(w.hdr));
+  make_scale_kernel<<<1, 1, 0, st>>>(w.hdr, 0);
+  // G = alpha sum_b L_b^T L_b over slabs of block rows; slab b = rows [r0, r1) touches G[0 .. r1)^2.
+  // Starting with the last slab, the first update of every tile is the one with gamma = 0.
+  const int nslab = static_cast<int>(ceil_div(nblk, nbb));
+  for (int b = nslab - 1; b >= 0; --b) {
+    const int b0 = b * nbb, b1 = (b + 1) * nbb < nblk ? (b + 1) * nbb : nblk;
+    const long long rows = static_cast<long long>(b1) * TS;  // non-zero columns of the slab
+    const int W = (b1 - b0) * TS;
+    const float* slab = L + static_cast<long long>(b0) * TS * ldl;
+    const float gamma = (b == nslab - 1) ? 0.f : 1.f;
+    exact_diag_t_kernel<<<static_cast<int>(ceil_div(rows, 256)), 256, 0, st>>>(
+        G, ldg, slab, ldl, rows, W, static_cast<long long>(b0) * TS, gamma, alpha, w.dsave);
+    split_f16_kernel<<<static_cast<int>(ceil_div(rows * (W / 8), 256)), 256, 0, st>>>(
+        slab, ldl, rows, W, 1, static_cast<long long>(b0) * TS, w.hdr, w.opA, w.opB);
+    SAB_CHECK_CUDA(cudaGetLastError());
+    if (int rc = tc_gemm_nt(stream, w.opA, rows, 3 * W, w.opB, rows, 3 * W, 3 * W, G, ldg, alpha * tc_gain(W),
+                            w.hdr + 2, gamma, 1))
+      return rc;
+    restore_diag_kernel<<<static_cast<int>(ceil_div(rows, 256)), 256, 0, st>>>(G, ldg, rows, w.dsave);
+  }
+  add_diag_kernel<<<static_cast<int>(ceil_div(M, 256)), 256, 0, st>>>(G, M, ldg, beta);
   SAB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

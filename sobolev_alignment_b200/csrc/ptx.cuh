@@ -341,6 +341,9 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void prefetch_l2(const void* addr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
+}
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }

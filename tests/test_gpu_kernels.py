@@ -227,9 +227,15 @@ def test_kernel_object_is_callable_like_falkon(cuda_ops):
 
 
 # ---------------------------------------------------------------------------- preconditioner algebra
-@pytest.mark.parametrize("M,dp", [(128, 4), (384, 12), (1024, 20), (2048, 32)])
-def test_cholesky_ltl_trsm(cuda_ops, M, dp):
+@pytest.mark.parametrize("M,dp,nb", [(128, 4, None), (384, 12, 128), (1024, 20, None), (2048, 32, 256), (2048, 20, "simt")])
+def test_cholesky_ltl_trsm(cuda_ops, M, dp, nb, monkeypatch):
+    """potrf / ltl on the tensor-core path (several outer panel widths) and on the fp32 SIMT path."""
     from sobolev_alignment_b200 import _native as nat
+
+    if nb == "simt":
+        monkeypatch.setenv("SAB_LINALG_SIMT", "1")
+    elif nb is not None:
+        monkeypatch.setenv("SAB_CHOL_NB", str(nb))
 
     g = torch.Generator().manual_seed(M)
     Z = torch.randn(M, 24, generator=g, dtype=torch.float64)
