@@ -110,9 +110,13 @@ int sa_add_diag(void* stream, float* A, int64_t M, int64_t lda, float value);
 /*
  * Triangular solves with a Cholesky factor from sa_potrf (cuBLAS `trsm` inside falkon's
  * `invT / invTt / invA / invAt` [ext]):  B[M x dp] <- L^-1 B (transpose = 0) or L^-T B (transpose = 1).
+ * One launch per solve; the block-to-block dependencies run through flags in `workspace` (caller-owned
+ * scratch of at least sa_trsm_workspace_bytes(M) bytes, 16-byte aligned; zeroed by the library on the
+ * same stream).
  */
+int64_t sa_trsm_workspace_bytes(int64_t M);
 int sa_trsm(void* stream, const float* L, int64_t M, int64_t ldl, const float* invdiag, float* B,
-            int dp, int transpose);
+            int dp, int transpose, void* workspace, int64_t workspace_bytes);
 
 /*
  * Conjugate-gradient vector kernels (falkon `ConjugateGradient.solve` [ext]); all M x dp fp32.

@@ -76,7 +76,8 @@ _SIGNATURES = {
     "sa_ltl": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p,
                        c_int64]),
     "sa_add_diag": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float]),
-    "sa_trsm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int]),
+    "sa_trsm_workspace_bytes": (c_int64, [c_int64]),
+    "sa_trsm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64]),
     "sa_coldot": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "sa_cg_update": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_float, c_void_p]),
@@ -280,13 +281,14 @@ def trsm(L: torch.Tensor, invdiag: torch.Tensor, B: torch.Tensor, transpose: boo
     if STATS.time_kmv:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
+    ws = _workspace(B.device, int(load().sa_trsm_workspace_bytes(L.shape[0])))
     _check(load().sa_trsm(_stream(), L.data_ptr(), L.shape[0], L.stride(0), invdiag.data_ptr(),
-                          B.data_ptr(), B.shape[1], int(transpose)))
+                          B.data_ptr(), B.shape[1], int(transpose), ws.data_ptr(), ws.numel()))
     if ev is not None:
         ev[1].record()
         m = L.shape[0]
         STATS.trsm_events.append((m * (m + TILE) / 2 * 4.0, ev[0], ev[1]))   # the triangle is read once
-    STATS.launches += L.shape[0] // TILE
+    STATS.launches += 1
     return B
 
 

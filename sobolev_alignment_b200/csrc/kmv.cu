@@ -85,11 +85,20 @@ constexpr float SNAP_FLOOR = 4.0e-7f;
 // bytes one CTA stages per 64-wide K block (its A tile + its share of the B tile) / per pipeline stage
 __host__ __device__ constexpr int sub_bytes(int cg) { return A_BYTES + B_BYTES / cg; }
 __host__ __device__ constexpr int stage_bytes(int cg) { return KSUB * sub_bytes(cg); }
-// N of the P V product (columns of V incl. padding); the 2-CTA TS form needs a multiple of 32
-__host__ __device__ constexpr int pv_n(int dp, int cg) { return (cg == 2 || dp > 16) ? 32 : 16; }
-// bytes of one V tile in the workspace: per CTA of the group a hi block followed by a lo block,
-// each PV_STEPS x (pv_n / cg) x 16 fp16
-__host__ __device__ constexpr int vtile_bytes(int dp, int cg) { return 2 * PV_STEPS * pv_n(dp, cg) * UMMA_K * 2; }
+// The P V product per 16 columns of the tile (one K step) is TWO tcgen05.mma (every small MMA costs
+// ~70 cycles of the tensor pipe whatever its N, measured):
+//   (a)  [O1 | O2] += P_hi [V_hi ; V_lo]^T     N = 64   (V_hi and V_lo stacked along N)
+//   (b)        O2  += P_lo  V_hi^T             N = 32
+// V tile in shared memory, per K step 8x8 core matrices, K-major, no swizzle (core (n/8, k/8) at
+// ((n/8) 2 + k/8) 128 B).  CG = 1: region X = [V_hi (32 columns) ; V_lo (32)] = 2048 B per step; (b)
+// reads the first half of X.  CG = 2: the B operand of a pair MMA is split by N halves between the
+// CTAs at the SAME shared-memory offset, so CTA 0 holds X = V_hi (32 columns), CTA 1 holds X = V_lo
+// (1024 B per step each), and a second region Y = V_hi[16 r, 16 r + 16) (512 B per step) feeds (b).
+constexpr int NP = 32;  // columns of the O accumulators (V columns incl. padding)
+__host__ __device__ constexpr int vx_bytes(int cg) { return (2 * NP / cg) * UMMA_K * 2; }
+__host__ __device__ constexpr int vy_bytes(int cg) { return cg == 2 ? (NP / 2) * UMMA_K * 2 : 0; }
+// bytes of one V tile per CTA: all X steps, then all Y steps
+__host__ __device__ constexpr int vcta_bytes(int cg) { return PV_STEPS * (vx_bytes(cg) + vy_bytes(cg)); }
 
 struct Params {
   long long a, b;  // rows of A / rows of B
@@ -111,7 +120,8 @@ struct Params {
   const float* alpha_dev;  // optional device-side factor of alpha (NULL = 1)
   int lower;           // MODE_GEMM: only tiles that touch the lower triangle (col <= row) are computed
   int debug;   // SAB_DEBUG bit mask, timing experiments only (results are garbage): 1 = no TMA
-               // loads after the first fill, 2 = epilogue skips its math, 4 = no P V products
+               // loads after the first fill, 2 = epilogue skips everything, 4 = no P V products,
+               // 8 = no tcgen05.st of P, 16 = no sqrt / exp
 };
 
 // what the kernel does with S = A B^T
@@ -192,12 +202,10 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr bool DENSE = MODE != MODE_KMV;  // no V tile, no P V product, S drained by the epilogue
   constexpr bool GEMM = MODE == MODE_GEMM;  // no norm tile either
-  constexpr int NP = pv_n(DP, CG);          // columns of the O accumulators
-  constexpr int NPC = NP / CG;              // V columns staged by this CTA
   constexpr int STAGE = stage_bytes(CG);
   constexpr int SUB = sub_bytes(CG);
-  constexpr int VT_BYTES = DENSE ? 0 : vtile_bytes(DP, CG) / CG;  // this CTA's share of a V tile
-  constexpr int VLO_OFF = VT_BYTES / 2;
+  constexpr int VT_BYTES = DENSE ? 0 : vcta_bytes(CG);  // this CTA's share of a V tile
+  constexpr int VX = vx_bytes(CG), VY = vy_bytes(CG);
   constexpr uint16_t PAIR_MASK = 3;         // cluster = exactly the CTA pair
   using Iter = TileIter<CG>;
   uint8_t* tiles = smem;
@@ -303,7 +311,8 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     // ====================================== MMA issuer ======================================
     if (lane == 0 && leader) {
       constexpr uint32_t idesc_s = umma_idesc_f16(BM * CG, BN);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(BM * CG, NP);
+      constexpr uint32_t idesc_pva = umma_idesc_f16(BM * CG, 2 * NP);
+      constexpr uint32_t idesc_pvb = umma_idesc_f16(BM * CG, NP);
       int s = 0;
       uint32_t ph = 0;
       // S = A B^T for one column tile into accumulator `buf`
@@ -361,16 +370,13 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           const uint32_t vs = smem_u32(vbuf + vb * VT_BYTES);
 #pragma unroll
           for (int st = 0; st < ((P.debug & 4) ? 0 : PV_STEPS); ++st) {
-            // V tile: per 16-column step NPC x 16 fp16, 8x8 core matrices, K-major, no swizzle:
-            // core (n/8, k/8) at ((n/8)*2 + k/8) * 128 B  ->  LBO (K) = 128 B, SBO (N) = 256 B
-            const uint64_t dhi = umma_smem_desc_noswz(vs + st * (NPC * 32), 128, 256);
-            const uint64_t dlo = umma_smem_desc_noswz(vs + VLO_OFF + st * (NPC * 32), 128, 256);
+            const uint64_t dx = umma_smem_desc_noswz(vs + st * VX, 128, 256);
+            const uint64_t dy = CG == 2 ? umma_smem_desc_noswz(vs + PV_STEPS * VX + st * VY, 128, 256) : dx;
             const uint32_t phi = tp + static_cast<uint32_t>(16 * st);  // 8 columns = 16 fp16 of hi
             const uint32_t plo = phi + 8;                               // then 8 columns of lo
             const uint32_t acc = (cur.first() && st == 0) ? 0u : 1u;
-            umma_f16_ts<CG>(tmem_base + TM_O1, phi, dhi, idesc_pv, acc);
-            umma_f16_ts<CG>(tmem_base + TM_O2, plo, dhi, idesc_pv, acc);
-            umma_f16_ts<CG>(tmem_base + TM_O2, phi, dlo, idesc_pv, 1u);
+            umma_f16_ts<CG>(tmem_base + TM_O1, phi, dx, idesc_pva, acc);  // [O1 | O2] (+)= P_hi [V_hi ; V_lo]^T
+            umma_f16_ts<CG>(tmem_base + TM_O2, plo, dy, idesc_pvb, 1u);   //       O2   += P_lo  V_hi^T
           }
           umma_commit<CG>(bar_vempty + 8 * vb, PAIR_MASK);
           if (cur.last()) umma_commit<CG>(bar_ofull, PAIR_MASK);
@@ -495,7 +501,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           const float nn = na + Ns[c0 + c];
           float d2 = fmaf(P.m2g, __uint_as_float(r[c]), nn);
           if (d2 < P.snap * nn || col0 + c0 + c == sym_row) d2 = 0.f;
-          kv[c] = kernel_value<KID>(d2, P.c0, DENSE ? 0.f : K_SCALE_LOG2);
+          kv[c] = (P.debug & 16) ? d2 : kernel_value<KID>(d2, P.c0, DENSE ? 0.f : K_SCALE_LOG2);
         }
         if (DENSE) {
           if (row_ok) {
@@ -522,7 +528,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             w[c / 2] = *reinterpret_cast<const uint32_t*>(&hi);
             w[8 + c / 2] = *reinterpret_cast<const uint32_t*>(&lo);
           }
-          tmem_st_32x16(tacc + static_cast<uint32_t>(c0), w);
+          if (!(P.debug & 8)) tmem_st_32x16(tacc + static_cast<uint32_t>(c0), w);
         }
       }
       if (!DENSE) tmem_wait_st();
@@ -539,13 +545,8 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           mbar_wait(bar_ofull, ophase);
           tcgen05_fence_after();
           uint32_t o1[NP], o2[NP];
-          if constexpr (NP == 32) {
-            tmem_ld_32x32(tmem_base + tlane + TM_O1, o1);
-            tmem_ld_32x32(tmem_base + tlane + TM_O2, o2);
-          } else {
-            tmem_ld_32x16(tmem_base + tlane + TM_O1, o1);
-            tmem_ld_32x16(tmem_base + tlane + TM_O2, o2);
-          }
+          tmem_ld_32x32(tmem_base + tlane + TM_O1, o1);
+          tmem_ld_32x32(tmem_base + tlane + TM_O2, o2);
           tmem_wait_ld();
           tcgen05_fence_before();
           __syncwarp();
@@ -591,22 +592,19 @@ __global__ void colmax_kernel(const float* __restrict__ V, long long b, int dp,
   atomicMax(maxbits + threadIdx.x, __float_as_uint(m));  // non-negative floats order like their bits
 }
 
-// one thread per 16-byte group = 8 consecutive K elements (rows of V) of one output column c.
-// Tile layout: for each CTA r of the group [hi block | lo block], each PV_STEPS x (np / cg) x 16 fp16
-// as K-major 8x8 core matrices; CTA r holds the columns [r np/cg, (r+1) np/cg).
-__global__ void vsplit_kernel(const float* __restrict__ V, long long b, int dp, int np, int cg, long long tb,
+// one thread per 16-byte group = 8 consecutive K elements (rows of V) of one output column c; writes
+// the hi / lo fp16 values into the X / Y regions of the tile (layout: see vx_bytes above)
+__global__ void vsplit_kernel(const float* __restrict__ V, long long b, int dp, int cg, long long tb,
                               const uint32_t* __restrict__ maxbits, uint8_t* __restrict__ tiles) {
-  const long long groups_per_tile = static_cast<long long>(PV_STEPS) * np * 2;
+  const long long groups_per_tile = static_cast<long long>(PV_STEPS) * NP * 2;
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= tb * groups_per_tile) return;
   const long long tile = gid / groups_per_tile;
   int rem = static_cast<int>(gid % groups_per_tile);
-  const int st = rem / (np * 2);
-  rem %= np * 2;
-  const int core = rem / 8;  // (n/8) * 2 + k/8 over the full np columns
-  const int nn = rem % 8;
-  const int c = (core >> 1) * 8 + nn;
-  const int kh = core & 1;
+  const int st = rem / (NP * 2);
+  rem %= NP * 2;
+  const int c = rem >> 1;  // V column
+  const int kh = rem & 1;  // which 8 of the step's 16 K elements
   float sc = 1.f, inv = 1.f;
   if (c < dp) column_scale(maxbits[c], &sc, &inv);
   __align__(16) __half hi[8];
@@ -618,14 +616,19 @@ __global__ void vsplit_kernel(const float* __restrict__ V, long long b, int dp, 
     hi[kk] = __float2half_rn(v);
     lo[kk] = __float2half_rn((v - __half2float(hi[kk])) * LO_GAIN);
   }
-  const int npc = np / cg;
-  const int r = c / npc, cl = c % npc;
-  const int tile_bytes = 2 * PV_STEPS * np * UMMA_K * 2;
-  const int cta_bytes = tile_bytes / cg;
-  const int core_local = (cl >> 3) * 2 + kh;
-  uint8_t* base = tiles + tile * tile_bytes + r * cta_bytes + st * (npc * 32) + core_local * 128 + nn * 16;
-  *reinterpret_cast<uint4*>(base) = *reinterpret_cast<const uint4*>(hi);
-  *reinterpret_cast<uint4*>(base + cta_bytes / 2) = *reinterpret_cast<const uint4*>(lo);
+  const uint4 H = *reinterpret_cast<const uint4*>(hi), L = *reinterpret_cast<const uint4*>(lo);
+  const int vx = vx_bytes(cg), vy = vy_bytes(cg), cta = vcta_bytes(cg);
+  uint8_t* t0 = tiles + tile * (static_cast<long long>(cg) * cta);
+  auto core_off = [](int n, int khalf) { return ((n >> 3) * 2 + khalf) * 128 + (n & 7) * 16; };
+  if (cg == 1) {
+    *reinterpret_cast<uint4*>(t0 + st * vx + core_off(c, kh)) = H;
+    *reinterpret_cast<uint4*>(t0 + st * vx + core_off(NP + c, kh)) = L;
+  } else {
+    *reinterpret_cast<uint4*>(t0 + st * vx + core_off(c, kh)) = H;        // CTA 0, region X = V_hi
+    *reinterpret_cast<uint4*>(t0 + cta + st * vx + core_off(c, kh)) = L;  // CTA 1, region X = V_lo
+    const int r = c / (NP / 2);                                           // region Y of CTA r = its half of V_hi
+    *reinterpret_cast<uint4*>(t0 + r * cta + PV_STEPS * vx + st * vy + core_off(c % (NP / 2), kh)) = H;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -780,7 +783,8 @@ static int launch_cg(cudaStream_t st, int kernel, const CUtensorMap& tmA, const 
 // the workspace is sized for the larger (2-CTA) V tile so that the launch-time choice of the CTA
 // group never changes what the caller has to provide
 int64_t workspace_bytes(int64_t b, int dp) {
-  return WS_HEADER_BYTES + ceil_div(b > 0 ? b : 1, BN) * static_cast<int64_t>(vtile_bytes(dp, 2));
+  (void)dp;
+  return WS_HEADER_BYTES + ceil_div(b > 0 ? b : 1, BN) * static_cast<int64_t>(2 * vcta_bytes(2));
 }
 
 int launch(void* stream, int kernel, float kscale, const void* A, const float* nA, int64_t a,
@@ -853,7 +857,7 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
 
   // shared memory plan: as many pipeline stages as fit, two V buffers when they fit too
   const int stage = stage_bytes(cg);
-  const int vbytes = (dense ? 0 : vtile_bytes(dp, cg) / cg) + NB_FLOATS * 4;
+  const int vbytes = (dense ? 0 : vcta_bytes(cg)) + NB_FLOATS * 4;
   const int fixed = 32 * 4 /*vinv*/ + NUM_BARS * 8 + 64;
   int stages = env_int("SAB_STAGES", MAX_STAGES);
   int vbufs = env_int("SAB_VBUFS", 2);
@@ -877,10 +881,9 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
     long long g = ceil_div(b, static_cast<int64_t>(rows) * 8);
     if (g > 1184) g = 1184;
     colmax_kernel<<<static_cast<int>(g), dim3(dp, rows), 0, st>>>(V, b, dp, maxbits);
-    const int np = pv_n(dp, cg);
-    const long long groups = static_cast<long long>(P.tb) * PV_STEPS * np * 2;
+    const long long groups = static_cast<long long>(P.tb) * PV_STEPS * NP * 2;
     vsplit_kernel<<<static_cast<int>(ceil_div(groups, 256)), 256, 0, st>>>(
-        V, b, dp, np, cg, P.tb, maxbits, static_cast<uint8_t*>(ws) + WS_HEADER_BYTES);
+        V, b, dp, cg, P.tb, maxbits, static_cast<uint8_t*>(ws) + WS_HEADER_BYTES);
     SAB_CHECK_CUDA(cudaGetLastError());
   }
 

@@ -543,6 +543,161 @@ trsm_step_kernel(const float* __restrict__ L, long long ldl, const float* __rest
 }
 
 // --------------------------------------------------------------------------------------------
+// Single-launch block triangular solve.  CTA c solves block row blk(c) (forward: c, backward:
+// nblk-1-c): it streams the tiles L(blk, src) of the blocks solved before it through a two-slot
+// cp.async ring, eliminates each x_src once it has been published (flag in global memory, release /
+// acquire at gpu scope), finally multiplies by the pre-inverted diagonal block and publishes its own
+// x.  When the NEXT dependency is already published -- always the case while a CTA works off the
+// blocks solved before it became resident -- its x is prefetched together with its tile, so such
+// steps cost one tile product and no exposed memory latency.  Logical CTA indices come from an
+// atomic ticket, so a CTA only ever waits for CTAs that have already started (no dependence on the
+// hardware's dispatch order).
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int DP, bool TRANS>
+__global__ void __launch_bounds__(256)
+trsm_chain_kernel(const float* __restrict__ L, long long ldl, const float* __restrict__ invdiag,
+                  float* __restrict__ Bm, int nblk, int* __restrict__ sync) {
+  constexpr int NB8 = (DP + 7) / 8;
+  constexpr int LT = trsm_ldt(TRANS);
+  constexpr int LX = trsm_ldx(NB8);
+  extern __shared__ __align__(16) float tsm[];
+  float* ring = tsm;                  // [2][128][LT]
+  float* xring = tsm + 2 * TS * LT;   // [2][128][LX]
+  __shared__ int s_ticket, s_next;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(sync, 1);
+  __syncthreads();
+  const int c = s_ticket;             // c blocks are solved before this one
+  const int blk = TRANS ? nblk - 1 - c : c;
+  int* flags = sync + 64;
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = (threadIdx.x >> 5) * 16;
+
+  auto src_of = [&](int d) { return TRANS ? nblk - 1 - d : d; };
+  auto issue_tile = [&](int d) {  // d < c: tile of dependency d; d == c: the inverted diagonal block
+    float* dst = ring + (d & 1) * TS * LT;
+    if (d < c) {
+      const int src = src_of(d);
+      const float* tile = TRANS ? L + static_cast<long long>(src) * TS * ldl + static_cast<long long>(blk) * TS
+                                : L + static_cast<long long>(blk) * TS * ldl + static_cast<long long>(src) * TS;
+      load_tile_128_async<TRANS>(tile, ldl, dst);
+    } else {
+      load_tile_128_async<TRANS>(invdiag + static_cast<long long>(blk) * TS * TS, TS, dst);
+    }
+  };
+  auto issue_x = [&](int d) {
+    const float* xsrc = Bm + static_cast<long long>(src_of(d)) * TS * DP;
+    float* xs = xring + (d & 1) * TS * LX;
+    for (int idx = threadIdx.x; idx < TS * (DP / 4); idx += 256)
+      cp_async_16(xs + (idx / (DP / 4)) * LX + (idx % (DP / 4)) * 4, xsrc + idx * 4);
+  };
+
+  // padded columns of the rhs tiles must be finite
+  if (LX > DP)
+    for (int idx = threadIdx.x; idx < 2 * TS * (LX - DP); idx += 256)
+      xring[(idx / (LX - DP)) * LX + DP + idx % (LX - DP)] = 0.f;
+  issue_tile(0);
+  cp_async_commit();
+
+  // this thread's fragment of the block of b: rows m0+g and m0+g+8, columns nb*8 + 2t, +1
+  float* b0 = Bm + (static_cast<long long>(blk) * TS + m0 + g) * DP;
+  float* b1 = b0 + 8 * DP;
+  float bfrag[NB8][4];
+#pragma unroll
+  for (int nb = 0; nb < NB8; ++nb) {
+    const int cc = nb * 8 + 2 * t;
+    float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+    if (cc < DP) {
+      v0 = *reinterpret_cast<const float2*>(b0 + cc);
+      v1 = *reinterpret_cast<const float2*>(b1 + cc);
+    }
+    bfrag[nb][0] = v0.x; bfrag[nb][1] = v0.y; bfrag[nb][2] = v1.x; bfrag[nb][3] = v1.y;
+  }
+
+  bool have_x = false;  // x of the current dependency was prefetched by the previous iteration
+  for (int d = 0; d < c; ++d) {
+    if (threadIdx.x == 0) {
+      if (!have_x) {
+        const int* f = flags + src_of(d);
+        unsigned spins = 0;
+        unsigned long long t0 = 0;
+        while (ld_acquire_gpu(f) == 0) {
+          if ((++spins & 0x3FFu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) {
+              printf("sobolev_b200: trsm chain timed out waiting for block %d (cta %d)\n", src_of(d), c);
+              __trap();
+            }
+          }
+        }
+      }
+      s_next = (d + 1 < c) ? ld_acquire_gpu(flags + src_of(d + 1)) : 0;
+    }
+    __syncthreads();  // x_src is published; everyone is done with slot (d + 1) & 1 of both rings
+    const bool nxt = s_next != 0;
+    if (!have_x) {
+      issue_x(d);
+      cp_async_commit();
+    }
+    issue_tile(d + 1);  // next dependency's tile (or the inverted diagonal block) streams meanwhile ...
+    if (nxt) issue_x(d + 1);  // ... with its x when that is already there
+    cp_async_commit();
+    cp_async_wait<1>();  // everything but that newest group: tile d and x_d have landed
+    __syncthreads();
+    float acc[NB8][4];
+    tile_times_rhs<NB8, TRANS>(ring + (d & 1) * TS * LT, xring + (d & 1) * TS * LX, acc);
+#pragma unroll
+    for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bfrag[nb][i] -= acc[nb][i];
+    have_x = nxt;
+  }
+  cp_async_wait<0>();
+  __syncthreads();  // inverted diagonal block landed; x ring free
+  float* xs = xring;
+#pragma unroll
+  for (int nb = 0; nb < NB8; ++nb) {
+    const int cc = nb * 8 + 2 * t;
+    xs[(m0 + g) * LX + cc] = bfrag[nb][0];
+    xs[(m0 + g) * LX + cc + 1] = bfrag[nb][1];
+    xs[(m0 + g + 8) * LX + cc] = bfrag[nb][2];
+    xs[(m0 + g + 8) * LX + cc + 1] = bfrag[nb][3];
+  }
+  __syncthreads();
+  float acc[NB8][4];
+  tile_times_rhs<NB8, TRANS>(ring + (c & 1) * TS * LT, xs, acc);
+#pragma unroll
+  for (int nb = 0; nb < NB8; ++nb) {
+    const int cc = nb * 8 + 2 * t;
+    if (cc < DP) {
+      *reinterpret_cast<float2*>(b0 + cc) = make_float2(acc[nb][0], acc[nb][1]);
+      *reinterpret_cast<float2*>(b1 + cc) = make_float2(acc[nb][2], acc[nb][3]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    st_release_gpu(flags + blk, 1);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
 // fp32 -> fp16 hi/lo operands of the tensor-core updates
 // --------------------------------------------------------------------------------------------
 constexpr int HDR_FLOATS = 64;  // workspace header: [0] max bits, [1] operand scale 2^s, [2] 2^-2s
@@ -765,8 +920,26 @@ static int red_grid(long long M, int rows_per_block) {
 
 template <int DP>
 static int trsm_launch(cudaStream_t st, const float* L, long long M, long long ldl, const float* invdiag,
-                       float* B, int transpose) {
+                       float* B, int transpose, int* sync) {
   const int nblk = static_cast<int>(M / TS);
+  const char* ev = std::getenv("SAB_TRSM_STEPS");
+  if (sync != nullptr && !(ev && std::atoi(ev) != 0)) {
+    // one launch: dependency chain through flags in `sync` ([0] ticket counter, [1 + i] block i solved)
+    // workspace: [0] ticket counter (64 ints reserved), then one flag per block
+    const int smem = (2 * TS * trsm_ldt(transpose != 0) + 2 * TS * trsm_ldx((DP + 7) / 8)) * static_cast<int>(sizeof(float));
+    SAB_CHECK_CUDA(cudaMemsetAsync(sync, 0, (64 + nblk) * sizeof(int), st));
+    if (transpose) {
+      auto kern = trsm_chain_kernel<DP, true>;
+      SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      kern<<<nblk, 256, smem, st>>>(L, ldl, invdiag, B, nblk, sync);
+    } else {
+      auto kern = trsm_chain_kernel<DP, false>;
+      SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      kern<<<nblk, 256, smem, st>>>(L, ldl, invdiag, B, nblk, sync);
+    }
+    SAB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int smem = (TS * trsm_ldt(transpose != 0) + TS * trsm_ldx((DP + 7) / 8)) * static_cast<int>(sizeof(float));
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(256);
@@ -962,20 +1135,26 @@ extern "C" int sa_add_diag(void* stream, float* A, int64_t M, int64_t lda, float
   return 0;
 }
 
+extern "C" int64_t sa_trsm_workspace_bytes(int64_t M) { return M <= 0 ? -1 : (64 + M / TS + 1) * 4; }
+
 extern "C" int sa_trsm(void* stream, const float* L, int64_t M, int64_t ldl, const float* invdiag,
-                       float* B, int dp, int transpose) {
+                       float* B, int dp, int transpose, void* workspace, int64_t workspace_bytes) {
   SAB_REQUIRE_MAT(M, ldl, L);
   SAB_REQUIRE(invdiag != nullptr && B != nullptr, "NULL operand");
+  SAB_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 &&
+                  workspace_bytes >= sa_trsm_workspace_bytes(M),
+              "workspace must hold sa_trsm_workspace_bytes(M) = %lld bytes", (long long)sa_trsm_workspace_bytes(M));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int* sync = static_cast<int*>(workspace);
   switch (dp) {
-    case 4: return trsm_launch<4>(st, L, M, ldl, invdiag, B, transpose);
-    case 8: return trsm_launch<8>(st, L, M, ldl, invdiag, B, transpose);
-    case 12: return trsm_launch<12>(st, L, M, ldl, invdiag, B, transpose);
-    case 16: return trsm_launch<16>(st, L, M, ldl, invdiag, B, transpose);
-    case 20: return trsm_launch<20>(st, L, M, ldl, invdiag, B, transpose);
-    case 24: return trsm_launch<24>(st, L, M, ldl, invdiag, B, transpose);
-    case 28: return trsm_launch<28>(st, L, M, ldl, invdiag, B, transpose);
-    case 32: return trsm_launch<32>(st, L, M, ldl, invdiag, B, transpose);
+    case 4: return trsm_launch<4>(st, L, M, ldl, invdiag, B, transpose, sync);
+    case 8: return trsm_launch<8>(st, L, M, ldl, invdiag, B, transpose, sync);
+    case 12: return trsm_launch<12>(st, L, M, ldl, invdiag, B, transpose, sync);
+    case 16: return trsm_launch<16>(st, L, M, ldl, invdiag, B, transpose, sync);
+    case 20: return trsm_launch<20>(st, L, M, ldl, invdiag, B, transpose, sync);
+    case 24: return trsm_launch<24>(st, L, M, ldl, invdiag, B, transpose, sync);
+    case 28: return trsm_launch<28>(st, L, M, ldl, invdiag, B, transpose, sync);
+    case 32: return trsm_launch<32>(st, L, M, ldl, invdiag, B, transpose, sync);
   }
   set_error("dp must be a multiple of 4 in [4, 32], got %d", dp);
   return 2;
