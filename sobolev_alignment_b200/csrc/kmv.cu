@@ -119,6 +119,7 @@ struct Params {
   float alpha, gamma;  // MODE_GEMM: out = gamma * out + alpha * alpha_dev[0] * A B^T
   const float* alpha_dev;  // optional device-side factor of alpha (NULL = 1)
   int lower;           // MODE_GEMM: only tiles that touch the lower triangle (col <= row) are computed
+  long long* trace;  // SAB_TRACE_PTR (developer tool): clock64 event log of CTA 0's MMA thread
   int debug;   // SAB_DEBUG bit mask, timing experiments only (results are garbage): 1 = no TMA
                // loads after the first fill, 2 = epilogue skips everything, 4 = no P V products,
                // 8 = no tcgen05.st of P, 16 = no sqrt / exp
@@ -309,32 +310,46 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
-    if (lane == 0 && leader) {
+    if (leader) {  // the whole warp runs the loops; one elected lane issues
       constexpr uint32_t idesc_s = umma_idesc_f16(BM * CG, BN);
       constexpr uint32_t idesc_pva = umma_idesc_f16(BM * CG, 2 * NP);
       constexpr uint32_t idesc_pvb = umma_idesc_f16(BM * CG, NP);
       int s = 0;
       uint32_t ph = 0;
+      int nev = 0;
+      auto ev = [&](int type) {
+        if (P.trace != nullptr && blockIdx.x == 0 && lane == 0 && nev < 2000) {
+          P.trace[2 * nev] = type;
+          P.trace[2 * nev + 1] = clock64();
+          ++nev;
+        }
+      };
       // S = A B^T for one column tile into accumulator `buf`
       auto issue_s = [&](int buf) {
         const uint32_t tacc = tmem_base + static_cast<uint32_t>(buf ? TM_S1 : TM_S0);
         for (int kb = 0; kb < P.kblocks; kb += KSUB) {
           const int nsub = min(KSUB, P.kblocks - kb);
+          ev(1);
           mbar_wait(bar_full + 8 * s, ph);
+          ev(2);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(tiles + s * STAGE);
-          for (int u = 0; u < nsub; ++u) {
-            const uint64_t da = umma_smem_desc_sw128(sa + u * SUB);
-            const uint64_t db = umma_smem_desc_sw128(sa + u * SUB + A_BYTES);
+          if (elect_one_sync()) {
+            for (int u = 0; u < nsub; ++u) {
+              const uint64_t da = umma_smem_desc_sw128(sa + u * SUB);
+              const uint64_t db = umma_smem_desc_sw128(sa + u * SUB + A_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              // advance 16 fp16 = 32 B along K inside the 128 B swizzle atom: +2 in 16-byte units
-              umma_f16_ss<CG>(tacc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                              idesc_s, (kb | u | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                // advance 16 fp16 = 32 B along K inside the 128 B swizzle atom: +2 in 16-byte units
+                umma_f16_ss<CG>(tacc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                                idesc_s, (kb | u | k) != 0 ? 1u : 0u);
+              }
             }
+            umma_commit<CG>(bar_empty + 8 * s, PAIR_MASK);  // stage reusable once these MMAs retire
+            if (kb + KSUB >= P.kblocks) umma_commit<CG>(bar_sfull + 8 * buf, PAIR_MASK);
           }
-          umma_commit<CG>(bar_empty + 8 * s, PAIR_MASK);  // stage reusable once these MMAs retire
-          if (kb + KSUB >= P.kblocks) umma_commit<CG>(bar_sfull + 8 * buf, PAIR_MASK);
+          __syncwarp();
+          ev(3);
           if (++s == P.stages) { s = 0; ph ^= 1; }
         }
       };
@@ -359,7 +374,9 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           const int buf = t & 1;
           // P(t) is in TMEM of both CTAs; every epilogue warp waited for its V(t) / norm tile before
           // writing P, so the V tiles of both CTAs have landed as well
+          ev(4);
           mbar_wait_cluster(bar_pready + 8 * buf, (t >> 1) & 1u);
+          ev(5);
           if (CG == 1) mbar_wait(bar_vfull + 8 * vb, vph);
           if (cur.first() && t != 0) {  // previous unit's O has been read out
             mbar_wait_cluster(bar_oempty, ophase);
@@ -368,18 +385,22 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           tcgen05_fence_after();
           const uint32_t tp = tmem_base + static_cast<uint32_t>(buf ? TM_S1 : TM_S0);
           const uint32_t vs = smem_u32(vbuf + vb * VT_BYTES);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int st = 0; st < ((P.debug & 4) ? 0 : PV_STEPS); ++st) {
-            const uint64_t dx = umma_smem_desc_noswz(vs + st * VX, 128, 256);
-            const uint64_t dy = CG == 2 ? umma_smem_desc_noswz(vs + PV_STEPS * VX + st * VY, 128, 256) : dx;
-            const uint32_t phi = tp + static_cast<uint32_t>(16 * st);  // 8 columns = 16 fp16 of hi
-            const uint32_t plo = phi + 8;                               // then 8 columns of lo
-            const uint32_t acc = (cur.first() && st == 0) ? 0u : 1u;
-            umma_f16_ts<CG>(tmem_base + TM_O1, phi, dx, idesc_pva, acc);  // [O1 | O2] (+)= P_hi [V_hi ; V_lo]^T
-            umma_f16_ts<CG>(tmem_base + TM_O2, plo, dy, idesc_pvb, 1u);   //       O2   += P_lo  V_hi^T
+            for (int st = 0; st < ((P.debug & 4) ? 0 : PV_STEPS); ++st) {
+              const uint64_t dx = umma_smem_desc_noswz(vs + st * VX, 128, 256);
+              const uint64_t dy = CG == 2 ? umma_smem_desc_noswz(vs + PV_STEPS * VX + st * VY, 128, 256) : dx;
+              const uint32_t phi = tp + static_cast<uint32_t>(16 * st);  // 8 columns = 16 fp16 of hi
+              const uint32_t plo = phi + 8;                               // then 8 columns of lo
+              const uint32_t acc = (cur.first() && st == 0) ? 0u : 1u;
+              umma_f16_ts<CG>(tmem_base + TM_O1, phi, dx, idesc_pva, acc);  // [O1 | O2] (+)= P_hi [V_hi ; V_lo]^T
+              umma_f16_ts<CG>(tmem_base + TM_O2, plo, dy, idesc_pvb, 1u);   //       O2   += P_lo  V_hi^T
+            }
+            umma_commit<CG>(bar_vempty + 8 * vb, PAIR_MASK);
+            if (cur.last()) umma_commit<CG>(bar_ofull, PAIR_MASK);
           }
-          umma_commit<CG>(bar_vempty + 8 * vb, PAIR_MASK);
-          if (cur.last()) umma_commit<CG>(bar_ofull, PAIR_MASK);
+          __syncwarp();
+          ev(6);
           if (ahead.valid(P)) {  // S(t+2) reuses the TMEM columns of P(t): in issue order behind P V(t)
             issue_s(buf);
             ahead.next(P);
@@ -843,6 +864,10 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   P.gamma = gamma;
   P.lower = lower;
   P.debug = env_int("SAB_DEBUG", 0);
+  {
+    const char* tp = std::getenv("SAB_TRACE_PTR");
+    P.trace = tp ? reinterpret_cast<long long*>(std::strtoull(tp, nullptr, 0)) : nullptr;
+  }
   {
     const float steps = static_cast<float>(P.kblocks * (BK / UMMA_K));
     const char* sv = std::getenv("SAB_SNAP");  // < 0 disables both corrections (calibration runs)

@@ -12,6 +12,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// One lane of a fully converged warp.  Role loops run warp-uniform and only the asynchronous-proxy
+// instructions (tcgen05.mma / commit, TMA) sit under this predicate: the compiler then keeps their
+// descriptor operands in uniform registers.  Under a divergent `lane == 0` branch it wraps every such
+// instruction in an ELECT / R2UR waterfall loop instead (~95 issue cycles per MMA, measured).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
