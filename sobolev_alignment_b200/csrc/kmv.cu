@@ -275,7 +275,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    {
       int s = 0;
       uint32_t ph = 0;
       bool filled = false;
@@ -285,25 +285,28 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           const int nsub = min(KSUB, P.kblocks - kb);
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           const uint32_t dst = smem_u32(tiles + s * STAGE);
-          if ((P.debug & 1) && filled) {  // timing experiment: the stages keep their first contents
-            if (leader) mbar_arrive(bar_full + 8 * s);
-          } else if constexpr (CG == 1) {
-            const uint32_t full = bar_full + 8 * s;
-            mbar_arrive_expect_tx(full, nsub * SUB);
-            for (int u = 0; u < nsub; ++u) {
-              tma_load_2d(dst + u * SUB, &tmA, full, (kb + u) * BK, rt * BM);
-              tma_load_2d(dst + u * SUB + A_BYTES, &tmB, full, (kb + u) * BK, it.j * BN);
-            }
-          } else {
-            // both CTAs fill their own stage; every byte is accounted on the leader's full barrier
-            if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, CG * nsub * SUB);
-            const uint32_t full = lead_full + 8 * s;
-            for (int u = 0; u < nsub; ++u) {
-              tma_load_2d_cg2(dst + u * SUB, &tmA, full, (kb + u) * BK, rt * BM);
-              tma_load_2d_cg2(dst + u * SUB + A_BYTES, &tmB, full, (kb + u) * BK,
-                              it.j * BN + crank * (BN / CG));
+          if (elect_one_sync()) {
+            if ((P.debug & 1) && filled) {  // timing experiment: the stages keep their first contents
+              if (leader) mbar_arrive(bar_full + 8 * s);
+            } else if constexpr (CG == 1) {
+              const uint32_t full = bar_full + 8 * s;
+              mbar_arrive_expect_tx(full, nsub * SUB);
+              for (int u = 0; u < nsub; ++u) {
+                tma_load_2d(dst + u * SUB, &tmA, full, (kb + u) * BK, rt * BM);
+                tma_load_2d(dst + u * SUB + A_BYTES, &tmB, full, (kb + u) * BK, it.j * BN);
+              }
+            } else {
+              // both CTAs fill their own stage; every byte is accounted on the leader's full barrier
+              if (leader) mbar_arrive_expect_tx(bar_full + 8 * s, CG * nsub * SUB);
+              const uint32_t full = lead_full + 8 * s;
+              for (int u = 0; u < nsub; ++u) {
+                tma_load_2d_cg2(dst + u * SUB, &tmA, full, (kb + u) * BK, rt * BM);
+                tma_load_2d_cg2(dst + u * SUB + A_BYTES, &tmB, full, (kb + u) * BK,
+                                it.j * BN + crank * (BN / CG));
+              }
             }
           }
+          __syncwarp();
           if (++s == P.stages) { s = 0; ph ^= 1; filled = true; }
         }
       }
@@ -411,25 +414,27 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     }
   } else if (warp == 2) {
     // ================================ V / norm tile loader ==================================
-    if (lane == 0 && !GEMM) {
+    if (!GEMM) {
       int vb = 0;
       uint32_t vph = 0;
       for (Iter it(P); it.valid(P); it.next(P)) {
-        mbar_wait(bar_vempty + 8 * vb, vph ^ 1);
+        mbar_wait_suspend(bar_vempty + 8 * vb, vph ^ 1);
         const long long col0 = static_cast<long long>(it.j) * BN;
         const int cols_valid = static_cast<int>(min(static_cast<long long>(BN), P.b - col0));
         const uint32_t nbytes = static_cast<uint32_t>((cols_valid + 3) & ~3) * 4u;
         const uint32_t full = bar_vfull + 8 * vb;
-        mbar_arrive_expect_tx(full, nbytes + VT_BYTES);
-        bulk_load_1d(smem_u32(nbuf + vb * NB_FLOATS), P.nB + col0, nbytes, full);
-        if (!DENSE)
-          bulk_load_1d(smem_u32(vbuf + vb * VT_BYTES),
-                       P.vws + WS_HEADER_BYTES + (static_cast<long long>(it.j) * CG + crank) * VT_BYTES,
-                       VT_BYTES, full);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(full, nbytes + VT_BYTES);
+          bulk_load_1d(smem_u32(nbuf + vb * NB_FLOATS), P.nB + col0, nbytes, full);
+          if (!DENSE)
+            bulk_load_1d(smem_u32(vbuf + vb * VT_BYTES),
+                         P.vws + WS_HEADER_BYTES + (static_cast<long long>(it.j) * CG + crank) * VT_BYTES,
+                         VT_BYTES, full);
+        }
+        __syncwarp();
         if (++vb == P.vbufs) { vb = 0; vph ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp >= FIRST_EPI_WARP) {
     // ======================================= epilogue =======================================
     const int e = warp - FIRST_EPI_WARP;
@@ -446,10 +451,12 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       const long long grow = static_cast<long long>(it.row_tile(P, crank)) * BM + row_in_tile;
       const bool row_ok = grow < P.a;
       const float na = row_ok ? __ldg(P.nA + grow) : 0.f;
-      const long long sym_row = P.symmetric ? grow : -1;
+      // column (inside this tile) of the exact-zero distance of a symmetric product, or -1
+      const long long sym_off = grow - static_cast<long long>(it.j) * BN;
+      const int sym_c = (P.symmetric && sym_off >= 0 && sym_off < BN) ? static_cast<int>(sym_off) : -1;
       const long long col0 = static_cast<long long>(it.j) * BN;
       const int cols_valid = static_cast<int>(min(static_cast<long long>(BN), P.b - col0));
-      if (!GEMM) mbar_wait(bar_vfull + 8 * vb, vph);
+      if (!GEMM) mbar_wait_suspend(bar_vfull + 8 * vb, vph);
       if (GEMM && row_ok && P.gamma != 0.f) {
         // the read-modify-write of C is what bounds this mode: pull this thread's 112 floats towards L2
         // while the MMAs of the tile are still running
@@ -458,7 +465,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         for (int q = 0; q < 4; ++q)
           if (cbeg + 32 * q < cols_valid) prefetch_l2(cp + 32 * q);
       }
-      mbar_wait(bar_sfull + 8 * buf, (t >> 1) & 1u);
+      mbar_wait_suspend(bar_sfull + 8 * buf, (t >> 1) & 1u);
       tcgen05_fence_after();
       const float* Ns = nbuf + vb * NB_FLOATS;
       const uint32_t tacc = tmem_base + tlane + static_cast<uint32_t>(buf ? TM_S1 : TM_S0);
@@ -521,7 +528,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         for (int c = 0; c < 16; ++c) {
           const float nn = na + Ns[c0 + c];
           float d2 = fmaf(P.m2g, __uint_as_float(r[c]), nn);
-          if (d2 < P.snap * nn || col0 + c0 + c == sym_row) d2 = 0.f;
+          if (d2 < P.snap * nn || c0 + c == sym_c) d2 = 0.f;
           kv[c] = (P.debug & 16) ? d2 : kernel_value<KID>(d2, P.c0, DENSE ? 0.f : K_SCALE_LOG2);
         }
         if (DENSE) {
@@ -563,7 +570,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       if (!DENSE && it.last()) {
         if (half == 0) {
           // the unit is complete once P V of its last tile has retired: read O out and add it
-          mbar_wait(bar_ofull, ophase);
+          mbar_wait_suspend(bar_ofull, ophase);
           tcgen05_fence_after();
           uint32_t o1[NP], o2[NP];
           tmem_ld_32x32(tmem_base + tlane + TM_O1, o1);

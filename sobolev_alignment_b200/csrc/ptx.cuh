@@ -61,6 +61,24 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// With a time hint (ns) try_wait suspends the warp in hardware until the phase completes or the hint
+// expires: a role that waits for long (the epilogue warps waiting for the next accumulator) costs no
+// issue slots -- and no power -- instead of spinning through a poll loop.  The wake-up is slower
+// than a poll, so the latency-critical waits (TMA <-> MMA) keep the plain form.
+constexpr uint32_t MBAR_SUSPEND_NS = 1000000u;
+__device__ __forceinline__ uint32_t mbar_try_wait_suspend(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_NS)
+      : "memory");
+  return ok;
+}
 // acquire at cluster scope: for barriers that receive mbar_arrive_cluster from the peer CTA
 __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -98,6 +116,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+__device__ __forceinline__ void mbar_wait_suspend(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait_suspend(bar, parity)) {
+    if ((++spins & 0x3Fu) == 0) {  // every failed try may have slept for the whole hint
+      uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {
+        printf("sobolev_b200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n",
+               blockIdx.x, threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait_cluster(bar, parity)) return;
   uint64_t t0 = 0;
