@@ -9,13 +9,20 @@ from sobolev_alignment_b200 import _native as nat  # noqa: E402
 
 dev = torch.device("cuda:0")
 mode = sys.argv[1] if len(sys.argv) > 1 else "fwd"
-rows = 148 * 128 * 2
+rows = int(os.environ.get("ROWS", 148 * 128 * 2))   # ROWS=1000000: the C3 launch shapes
 a, b = (rows, 50000) if mode == "fwd" else (50000, rows)
 p, d = 3000, 20
-A = torch.randn(a, p, device=dev) * 0.2
-B = torch.randn(b, p, device=dev) * 0.2
-PA, PB = nat.prep(A, None, None, 1.0), nat.prep(B, None, None, 1.0)
-del A, B
+
+
+def prepared(n):
+    out = nat.alloc_prepared(n, p, dev)
+    for s0 in range(0, n, 65536):
+        e0 = min(n, s0 + 65536)
+        nat.prep(torch.randn(e0 - s0, p, device=dev) * 0.2, None, None, 1.0, out=out, row_offset=s0)
+    return out
+
+
+PA, PB = prepared(a), prepared(b)
 V = torch.randn(b, d, device=dev)
 out = torch.zeros(a, d, device=dev)
 for i in range(3):
