@@ -105,6 +105,8 @@ struct Params {
   int kblocks;     // p_pad / 64
   int ta, tb;      // row tiles, column tiles
   int nsplit;      // column chunks per row tile
+  int cbs;         // chunks per chunk block: units are ordered (chunk block, row-tile group, chunk in
+                   // block), so the CTA pairs running together share `cbs` chunks of B; nsplit % cbs == 0
   int units;       // ceil(ta / CG) * nsplit
   int stages, vbufs;
   const float* nA;
@@ -157,15 +159,27 @@ __device__ __forceinline__ void column_scale(uint32_t maxbits, float* scale, flo
 template <int CG>
 struct TileIter {
   int unit, j, j0, j1;
-  // row-tile group of the current unit; lower-triangular sweeps start with the longest rows
-  __device__ __forceinline__ int group(const Params& P) const {
-    const int g = unit / P.nsplit;
-    return P.lower ? P.units / P.nsplit - 1 - g : g;
+  // unit -> (row-tile group, column chunk).  Units are ordered chunk block by chunk block, inside a
+  // block row-tile group by group with the block's `cbs` chunks fastest: the pairs running together
+  // cover sms / (CG cbs) row-tile groups x cbs chunks, their A strips stay L2 resident, the pairs on a
+  // chunk sweep the same B tiles in step, and a chunk is short enough that they cannot drift apart by
+  // more than L2 holds (long chunks made the transposed product re-read X from DRAM 5 times).
+  int g_, ch_;
+  __device__ __forceinline__ void decode(const Params& P) {
+    const int groups = P.units / P.nsplit;
+    const int per_block = groups * P.cbs;
+    const int cb = unit / per_block;
+    const int rem = unit - cb * per_block;
+    const int g = rem / P.cbs;
+    ch_ = cb * P.cbs + (rem - g * P.cbs);
+    g_ = P.lower ? groups - 1 - g : g;  // lower-triangular sweeps start with the longest rows
   }
+  __device__ __forceinline__ int group(const Params&) const { return g_; }
   // column range of the current unit; units left empty by the triangle are skipped
   __device__ __forceinline__ void set_range(const Params& P) {
     while (unit < P.units) {
-      const int ch = unit % P.nsplit;
+      decode(P);
+      const int ch = ch_;
       j0 = static_cast<int>(static_cast<long long>(ch) * P.tb / P.nsplit);
       j1 = static_cast<int>(static_cast<long long>(ch + 1) * P.tb / P.nsplit);
       if (P.lower) {  // column tiles entirely right of the unit's last row are not computed
@@ -178,7 +192,7 @@ struct TileIter {
     j = j0;
   }
   __device__ __forceinline__ explicit TileIter(const Params& P)
-      : unit(static_cast<int>(blockIdx.x) / CG), j(0), j0(0), j1(0) {
+      : unit(static_cast<int>(blockIdx.x) / CG), j(0), j0(0), j1(0), g_(0), ch_(0) {
     set_range(P);
   }
   __device__ __forceinline__ bool valid(const Params& P) const { return unit < P.units; }
@@ -726,11 +740,18 @@ static int env_int(const char* name, int dflt) {
   return v ? std::atoi(v) : dflt;
 }
 
-// cost model: waves x (column tiles per unit + fixed per-unit overhead), subject to the A strips of
-// the concurrently running row tiles fitting an L2 budget
-static int choose_nsplit(int ta, int tb, int sms, long long p_pad) {
+// Work decomposition of the fused product.  cbs = number of column chunks that are swept concurrently,
+// the smallest that keeps the A strips of the concurrently running row-tile groups inside an L2 budget;
+// nsplit = total number of chunks: at least what balances the units over the CTA pairs (cost model:
+// waves x (column tiles per unit + fixed per-unit overhead)), and enough that a chunk is at most
+// ~64 column tiles long.
+static void choose_split(int ta, int tb, int sms, long long p_pad, int* nsplit, int* cbs) {
   int forced = env_int("SAB_NSPLIT", 0);
-  if (forced > 0) return forced < tb ? forced : tb;
+  if (forced > 0) {
+    *nsplit = forced < tb ? forced : tb;
+    *cbs = *nsplit;
+    return;
+  }
   const double l2_budget = static_cast<double>(env_int("SAB_L2_BUDGET_MB", 32)) * 1048576.0;
   const double strip = static_cast<double>(BM) * static_cast<double>(p_pad) * 2.0;
   const int live = ta < sms ? ta : sms;
@@ -749,7 +770,16 @@ static int choose_nsplit(int ta, int tb, int sms, long long p_pad) {
       best_ns = ns;
     }
   }
-  return best_ns;
+  const int chunk_tiles = env_int("SAB_CHUNK_TILES", 64);
+  int ns = static_cast<int>(ceil_div(tb, chunk_tiles));
+  if (ns < best_ns) ns = best_ns;
+  if (ns > min_ns) ns = static_cast<int>(ceil_div(ns, min_ns)) * min_ns;  // whole chunk blocks
+  if (ns > tb) {  // cannot happen for tb >= min_ns^2; fall back to one block
+    ns = best_ns;
+    min_ns = ns;
+  }
+  *nsplit = ns;
+  *cbs = ns > min_ns ? min_ns : ns;
 }
 
 template <int KID, int DP, int MODE, int CG>
@@ -857,8 +887,14 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   // CTA pairs (cta_group::2): two row tiles per tcgen05.mma, each CTA stages half of every B tile
   const int cg = (env_int("SAB_CTA_GROUP", 2) >= 2 && P.ta >= 2 && di.sms >= 2) ? 2 : 1;
   const int ta_units = static_cast<int>(ceil_div(P.ta, cg));
-  if (mode == MODE_GEMM) P.nsplit = static_cast<int>(ceil_div(P.tb, env_int("SAB_GEMM_CHUNK", 8)));  // no reduction across column tiles: short units balance the triangle
-  else P.nsplit = dense ? 1 : choose_nsplit(ta_units, P.tb, di.sms / cg, p_pad * cg);
+  if (mode == MODE_GEMM) {  // no reduction across column tiles: short units balance the triangle
+    P.nsplit = static_cast<int>(ceil_div(P.tb, env_int("SAB_GEMM_CHUNK", 8)));
+    P.cbs = P.nsplit;
+  } else if (dense) {
+    P.nsplit = P.cbs = 1;
+  } else {
+    choose_split(ta_units, P.tb, di.sms / cg, p_pad * cg, &P.nsplit, &P.cbs);
+  }
   P.units = ta_units * P.nsplit;
   P.nA = nA;
   P.nB = nB;
