@@ -69,6 +69,8 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float K_SCALE_LOG2 = 14.f;   // k values are carried as k * 2^14 in fp16
 constexpr float LO_GAIN = 2048.f;      // the fp16 residual is carried as (x - hi) * 2^11
 constexpr int WS_HEADER_BYTES = 256;   // per-column max |V| (32 floats) + padding
+constexpr int GST_LD = 36;             // floats per row of the MODE_GEMM staging tile (32 + pad, 16 B aligned)
+constexpr int GST_BYTES = EPI_WARPS * 32 * GST_LD * 4;
 
 // The tcgen05 fp32 accumulator is not round-to-nearest: every K=16 MMA step truncates ~2^-22.4 of the
 // running sum.  For rows that coincide (every Nystrom centre is also a training row) the products
@@ -229,6 +231,8 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   float* vinv = nbuf + P.vbufs * NB_FLOATS;  // [32] 2^-14 / column scale
   uint64_t* bars = reinterpret_cast<uint64_t*>(vinv + 32);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+  // MODE_GEMM: per epilogue warp a [32 rows][GST_LD] fp32 staging tile (16-byte aligned behind the slot)
+  float* gstage = reinterpret_cast<float*>(tmem_slot + 4);
 
   const uint32_t bar_full = smem_u32(bars + 0);                      // [8] TMA -> MMA (leader's are used)
   const uint32_t bar_empty = smem_u32(bars + MAX_STAGES);            // [8] MMA -> TMA (each CTA its own)
@@ -471,64 +475,67 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       const long long col0 = static_cast<long long>(it.j) * BN;
       const int cols_valid = static_cast<int>(min(static_cast<long long>(BN), P.b - col0));
       if (!GEMM) mbar_wait_suspend(bar_vfull + 8 * vb, vph);
-      if (GEMM && row_ok && P.gamma != 0.f) {
-        // the read-modify-write of C is what bounds this mode: pull this thread's 112 floats towards L2
-        // while the MMAs of the tile are still running
-        const float* cp = P.out + grow * P.ldo + col0 + cbeg;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (cbeg + 32 * q < cols_valid) prefetch_l2(cp + 32 * q);
-      }
       mbar_wait_suspend(bar_sfull + 8 * buf, (t >> 1) & 1u);
       tcgen05_fence_after();
       const float* Ns = nbuf + vb * NB_FLOATS;
       const uint32_t tacc = tmem_base + tlane + static_cast<uint32_t>(buf ? TM_S1 : TM_S0);
       if constexpr (GEMM) {
-        // out = gamma out + alpha S.  Rows of this tile end at tile_last: column chunks right of it are
-        // above the diagonal band and left alone.  The loads of the next chunk's C values are issued
-        // before the current chunk is processed (the read-modify-write is latency bound otherwise).
-        const long long tile_last = static_cast<long long>(it.row_tile(P, crank) + 1) * BM - 1;
+        // out = gamma out + alpha S.  A TMEM lane is a row, so reading S gives every lane a different
+        // row of C -- 32 cache lines per load / store instruction.  The chunk is therefore transposed
+        // through shared memory: 8 lanes then cover one 128-byte row segment and a 128-bit global access
+        // touches 4 lines (the uncoalesced form spent ~14k LSU cycles per tile against 10.8k of MMAs).
+        // Rows of this tile end at tile_last: column chunks right of it are above the diagonal band and
+        // left alone.  The C loads of a chunk are issued before its S values are fetched from TMEM.
+        const long long tile_row0 = static_cast<long long>(it.row_tile(P, crank)) * BM;
+        const long long tile_last = tile_row0 + BM - 1;
         int cend = min(cbeg + HALF_COLS, cols_valid);
         if (P.lower) cend = static_cast<int>(min(static_cast<long long>(cend), tile_last - col0 + 1));
         const float alpha = P.alpha_dev ? P.alpha * __ldg(P.alpha_dev) : P.alpha;
         const bool rmw = P.gamma != 0.f;
-        float* rowp = P.out + grow * P.ldo + col0;
-        float4 nv[4];
-        auto load_chunk = [&](int c0) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            nv[q] = (rmw && row_ok && c0 + 16 <= cend) ? reinterpret_cast<const float4*>(rowp + c0)[q]
-                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-        };
-        if (cbeg < cend) load_chunk(cbeg);
+        float* st = gstage + e * 32 * GST_LD;
+        const int rsub = lane >> 3, colq = lane & 7;  // coalesced phase: 4 rows x 8 float4 per instruction
+        const long long wrow0 = tile_row0 + quarter * 32;
 #pragma unroll 1
-        for (int c0 = cbeg; c0 < cend; c0 += 16) {
-          float4 cv[4];
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+          const int w = min(32, cend - c0);  // 32, or 16 for the last chunk of the 112 columns
+          const bool col_ok = 4 * colq + 4 <= w;
+          float4 cv[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) cv[q] = nv[q];
-          if (c0 + 16 < cend) load_chunk(c0 + 16);
-          uint32_t r[16];
-          tmem_ld_32x16(tacc + static_cast<uint32_t>(c0), r);
-          tmem_wait_ld();
-          if (!row_ok) continue;
-          float* dst = rowp + c0;
-          if (c0 + 16 <= cend) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              cv[q].x = fmaf(alpha, __uint_as_float(r[4 * q + 0]), P.gamma * cv[q].x);
-              cv[q].y = fmaf(alpha, __uint_as_float(r[4 * q + 1]), P.gamma * cv[q].y);
-              cv[q].z = fmaf(alpha, __uint_as_float(r[4 * q + 2]), P.gamma * cv[q].z);
-              cv[q].w = fmaf(alpha, __uint_as_float(r[4 * q + 3]), P.gamma * cv[q].w);
-              reinterpret_cast<float4*>(dst)[q] = cv[q];
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 16; ++c)
-              if (c0 + c < cend) {
-                const float old = rmw ? dst[c] : 0.f;
-                dst[c] = fmaf(alpha, __uint_as_float(r[c]), P.gamma * old);
-              }
+          for (int q = 0; q < 8; ++q) {
+            const long long r = wrow0 + 4 * q + rsub;
+            cv[q] = (rmw && col_ok && r < P.a)
+                        ? *reinterpret_cast<const float4*>(P.out + r * P.ldo + col0 + c0 + 4 * colq)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+          uint32_t r32[32];
+          if (w == 32) {
+            tmem_ld_32x32(tacc + static_cast<uint32_t>(c0), r32);
+          } else {
+            uint32_t r16[16];
+            tmem_ld_32x16(tacc + static_cast<uint32_t>(c0), r16);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { r32[c] = r16[c]; r32[16 + c] = 0u; }
+          }
+          tmem_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(st + lane * GST_LD + 4 * q) =
+                make_uint4(r32[4 * q], r32[4 * q + 1], r32[4 * q + 2], r32[4 * q + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const long long r = wrow0 + 4 * q + rsub;
+            if (col_ok && r < P.a) {
+              const float4 sv = *reinterpret_cast<const float4*>(st + (4 * q + rsub) * GST_LD + 4 * colq);
+              float4 o;
+              o.x = fmaf(alpha, sv.x, P.gamma * cv[q].x);
+              o.y = fmaf(alpha, sv.y, P.gamma * cv[q].y);
+              o.z = fmaf(alpha, sv.z, P.gamma * cv[q].z);
+              o.w = fmaf(alpha, sv.w, P.gamma * cv[q].w);
+              *reinterpret_cast<float4*>(P.out + r * P.ldo + col0 + c0 + 4 * colq) = o;
+            }
+          }
+          __syncwarp();
         }
       }
 #pragma unroll 1
@@ -578,6 +585,7 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       __syncwarp();
       if (lane == 0) {
         if (CG == 1) mbar_arrive(bar_pready + 8 * buf);
+        else if (DENSE) mbar_arrive_cluster_relaxed(lead_pready + 8 * buf);  // "S drained": no data to publish
         else mbar_arrive_cluster(lead_pready + 8 * buf);
         if (!GEMM) mbar_arrive(bar_vempty + 8 * vb);
       }
@@ -861,7 +869,8 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   SAB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(nB) & 15) == 0,
               "operands must be 16-byte aligned");
-  SAB_REQUIRE(mode != MODE_GEMM || (ldo % 4 == 0), "GEMM output row stride must be a multiple of 4");
+  SAB_REQUIRE(mode != MODE_GEMM || (ldo % 4 == 0 && b % 16 == 0),
+              "GEMM output row stride must be a multiple of 4 and the column count a multiple of 16");
   SAB_REQUIRE(a < (1ll << 31) && b < (1ll << 31), "row counts must fit in int32");
   if (!dense) {
     SAB_REQUIRE(V != nullptr && out != nullptr, "V / out must not be NULL");
@@ -888,8 +897,13 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   const int cg = (env_int("SAB_CTA_GROUP", 2) >= 2 && P.ta >= 2 && di.sms >= 2) ? 2 : 1;
   const int ta_units = static_cast<int>(ceil_div(P.ta, cg));
   if (mode == MODE_GEMM) {  // no reduction across column tiles: short units balance the triangle
-    P.nsplit = static_cast<int>(ceil_div(P.tb, env_int("SAB_GEMM_CHUNK", 8)));
-    P.cbs = P.nsplit;
+    // chunk blocks of 4 x 8 column tiles: the B rows of a block (<= 32 x 224 rows) stay in L2 while the
+    // row-tile groups sweep past them; with all chunks in one block every row group re-read all of B
+    const int chunk = env_int("SAB_GEMM_CHUNK", 8);
+    const int cbs = env_int("SAB_GEMM_CBS", 4);
+    P.nsplit = static_cast<int>(ceil_div(ceil_div(P.tb, chunk), cbs)) * cbs;
+    if (P.nsplit > P.tb) P.nsplit = P.tb;
+    P.cbs = P.nsplit % cbs == 0 ? cbs : P.nsplit;
   } else if (dense) {
     P.nsplit = P.cbs = 1;
   } else {
@@ -926,7 +940,7 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   // shared memory plan: as many pipeline stages as fit, two V buffers when they fit too
   const int stage = stage_bytes(cg);
   const int vbytes = (dense ? 0 : vcta_bytes(cg)) + NB_FLOATS * 4;
-  const int fixed = 32 * 4 /*vinv*/ + NUM_BARS * 8 + 64;
+  const int fixed = 32 * 4 /*vinv*/ + NUM_BARS * 8 + 64 + (mode == MODE_GEMM ? GST_BYTES : 0);
   int stages = env_int("SAB_STAGES", MAX_STAGES);
   int vbufs = env_int("SAB_VBUFS", 2);
   if (stages > MAX_STAGES) stages = MAX_STAGES;

@@ -254,40 +254,39 @@ diag_factor_kernel(float* __restrict__ A, long long lda, int k, float* __restric
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[i][j] = Ls[(ty + 16 * i) * LDD + tx + 16 * j];
 
-  // ---- right-looking Cholesky: after step j, column j of `a` holds L[:, j]
-  for (int j = 0; j < TS; ++j) {
-    float* cb = colb + (j & 1) * TS;
-    const int jb = j >> 4, jx = j & 15;
-    if (tx == jx) {
+  // ---- right-looking Cholesky: after step j, column j of `a` holds L[:, j].  The column loop is split
+  // as j = 16 jb + jx with jb unrolled, so that every register index and most ownership tests are
+  // compile-time (a runtime `b == j / 16` costs an indexed branch per step).
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+  for (int jb = 0; jb < 8; ++jb) {
+#pragma unroll 1
+    for (int jx = 0; jx < 16; ++jx) {
+      const int j = jb * 16 + jx;
+      float* cb = colb + (j & 1) * TS;
+      if (tx == jx) {
 #pragma unroll
-        for (int b = 0; b < 8; ++b)
-          if (b == jb) cb[ty + 16 * i] = a[i][b];
-    }
-    __syncthreads();
-    const float piv = cb[j];
-    if (tid == 0 && !(piv > 0.f)) atomicCAS(info, 0, k * TS + j + 1);
-    const float d = sqrtf(fmaxf(piv, 1e-30f));
-    const float inv = 1.f / d;
-    float li[8], lc[8];
+        for (int i = jb; i < 8; ++i) cb[ty + 16 * i] = a[i][jb];  // rows >= 16 jb: all that is needed
+      }
+      __syncthreads();
+      const float piv = cb[j];
+      if (tid == 0 && !(piv > 0.f)) atomicCAS(info, 0, k * TS + j + 1);
+      const float inv = rsqrtf(fmaxf(piv, 1e-30f));
+      float li[8], lc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) li[i] = (ty + 16 * i > j) ? cb[ty + 16 * i] * inv : 0.f;
+      for (int i = jb; i < 8; ++i) li[i] = (i > jb || ty > jx) ? cb[ty + 16 * i] * inv : 0.f;
 #pragma unroll
-    for (int b = 0; b < 8; ++b) lc[b] = (tx + 16 * b > j) ? cb[tx + 16 * b] * inv : 0.f;
+      for (int b = jb; b < 8; ++b) lc[b] = (b > jb || tx > jx) ? cb[tx + 16 * b] * inv : 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+      for (int i = jb; i < 8; ++i)
 #pragma unroll
-      for (int b = 0; b < 8; ++b) a[i][b] = fmaf(-li[i], lc[b], a[i][b]);
-    if (tx == jx) {  // column j itself becomes L[:, j]
+        for (int b = jb; b < 8; ++b) a[i][b] = fmaf(-li[i], lc[b], a[i][b]);
+      if (tx == jx) {  // column j itself becomes L[:, j]
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int b = 0; b < 8; ++b)
-          if (b == jb) {
-            const int r = ty + 16 * i;
-            a[i][b] = r > j ? li[i] : (r == j ? d : a[i][b]);
-          }
+        for (int i = jb; i < 8; ++i) {
+          if (i > jb || ty > jx) a[i][jb] = li[i];
+          else if (ty == jx) a[i][jb] = piv * inv;  // sqrt(piv)
+        }
+      }
     }
   }
   __syncthreads();
@@ -311,30 +310,31 @@ diag_factor_kernel(float* __restrict__ A, long long lda, int k, float* __restric
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int b = 0; b < 8; ++b) a[i][b] = (ty + 16 * i == tx + 16 * b) ? 1.f : 0.f;
-  for (int j = 0; j < TS; ++j) {
-    float* rb = rowb + (j & 1) * TS;
-    const int jb = j >> 4, jy = j & 15;
-    const float dinv = 1.f / Ls[j * LDD + j];
-    if (ty == jy) {  // finish row j and broadcast it
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+  for (int jb = 0; jb < 8; ++jb) {
+#pragma unroll 1
+    for (int jy = 0; jy < 16; ++jy) {
+      const int j = jb * 16 + jy;
+      float* rb = rowb + (j & 1) * TS;
+      const float dinv = 1.f / Ls[j * LDD + j];
+      if (ty == jy) {  // finish row j and broadcast it (X is lower triangular: columns <= j)
 #pragma unroll
-        for (int b = 0; b < 8; ++b)
-          if (i == jb) {
-            a[i][b] *= dinv;
-            rb[tx + 16 * b] = a[i][b];
-          }
+        for (int b = 0; b <= jb; ++b) {
+          a[jb][b] *= dinv;
+          rb[tx + 16 * b] = a[jb][b];
+        }
+      }
+      __syncthreads();
+      float li[8], xr[8];
+#pragma unroll
+      for (int i = jb; i < 8; ++i) li[i] = (i > jb || ty > jy) ? Ls[(ty + 16 * i) * LDD + j] : 0.f;
+#pragma unroll
+      for (int b = 0; b <= jb; ++b) xr[b] = rb[tx + 16 * b];
+#pragma unroll
+      for (int i = jb; i < 8; ++i)
+#pragma unroll
+        for (int b = 0; b <= jb; ++b) a[i][b] = fmaf(-li[i], xr[b], a[i][b]);
     }
-    __syncthreads();
-    float li[8], xr[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) li[i] = (ty + 16 * i > j) ? Ls[(ty + 16 * i) * LDD + j] : 0.f;
-#pragma unroll
-    for (int b = 0; b < 8; ++b) xr[b] = rb[tx + 16 * b];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int b = 0; b < 8; ++b) a[i][b] = fmaf(-li[i], xr[b], a[i][b]);
   }
   __syncthreads();
 #pragma unroll

@@ -204,6 +204,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// Same without ordering of this thread's earlier memory operations.  For arrivals that only say "I am
+// done READING tensor memory" (tcgen05.wait::ld has already completed the reads): a release here would
+// first drain the thread's outstanding global stores (MEMBAR, ~13 % of the GEMM-mode samples).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 // 2-D tiled load issued by either CTA of a cta_group::2 pair into its OWN shared memory; the
 // complete_tx goes to `cluster_bar`, which may be the leader CTA's barrier (mapa_shared address).
 __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst_smem, const void* tmap, uint32_t cluster_bar,

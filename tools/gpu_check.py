@@ -184,7 +184,7 @@ def bench_linalg():
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) * 1e-3
 
-    for M in (2048, 16384, 32768, 50048):
+    for M in [int(x) for x in os.environ.get("BENCH_M", "2048,16384,32768,50048").split(",")]:
         g = torch.Generator(device=dev).manual_seed(1)
         Z = torch.randn(M, 64, device=dev, generator=g)
         A = torch.cdist(Z, Z)
