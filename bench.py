@@ -47,6 +47,11 @@ WORKLOADS = {
     "C4": (2_000_000, 3000, 100_000, 20, "matern", {"sigma": 10.0, "nu": 1.5}, 1e-6),
 }
 MAXITER = 20
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel (ncu --set full), mean of the
+# forward (77.3 GB) and transposed (87.9 GB) C3 launches; the tensor-bound kernel re-reads its fp16 operands
+# (6.3 GB) ~13 times through L2-sized windows, which is 5 % of the HBM bandwidth over the launch
+KMV_TRAFFIC = {("C3", 1): 82.6e9}
+KMV_TRAFFIC_SOURCE = "profiles/r01_kmv_v9_c3_ncu.txt + r01_kmv_v8_c3_*_ncu_full.txt (bytes per launch)"
 
 
 def measured_peaks():
@@ -303,7 +308,8 @@ def main():
         "config": workload_config(cfg_name, world),
         "roofline": {"bound": "tensor", "kernel": "kmv_kernel (fused tcgen05 K(A,B)@V)", "achieved": kmv_tflops,
                      "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": kmv_tflops / peaks["bf16_sustained"], "traffic": None,
+                     "frac": kmv_tflops / peaks["bf16_sustained"], "traffic": KMV_TRAFFIC.get((cfg_name, world)),
+                     "traffic_source": KMV_TRAFFIC_SOURCE if (cfg_name, world) in KMV_TRAFFIC else None,
                      "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                      "launches_timed": kmv_n, "kmv_seconds_per_fit": kmv_s / max(1, args.steps),
                      "algorithmic_flops_per_fit": kmv_flops / max(1, args.steps)},

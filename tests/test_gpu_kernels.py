@@ -259,6 +259,40 @@ def test_cholesky_ltl_trsm(cuda_ops, M, dp, nb, monkeypatch):
         assert relerr(X, ref) < 5e-5
 
 
+def test_large_factorisation_and_chained_solves(cuda_ops):
+    """
+    M = 24 576 = 192 blocks: more CTAs than SMs in the single-launch triangular solve (late blocks start
+    with a backlog of published dependencies), 48 outer panels in the tensor-core Cholesky.  Checked
+    against float64 on the device.
+    """
+    from sobolev_alignment_b200 import _native as nat
+
+    M, dp = 24576, 20
+    g = torch.Generator(device="cuda").manual_seed(3)
+    Z = torch.randn(M, 32, device="cuda", generator=g)
+    K = torch.cdist(Z, Z).mul_(-1.0 / 7.0).exp_()
+    K.diagonal().add_(1e-5 * M)
+    A = K.clone()
+    inv = torch.empty(M // 128, 128, 128, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    nat.potrf(A, inv, info)
+    assert int(info) == 0
+    L = torch.tril(A).double()
+    del A
+    # reconstruction error of the factor, relative to |K|
+    R = L @ L.T
+    R -= K.double()
+    assert float(R.abs().max()) < 2e-5
+    del R
+    B = torch.randn(M, dp, device="cuda", generator=g)
+    Lf = L.float().contiguous()
+    for tr in (False, True):
+        X = B.clone()
+        nat.trsm(Lf, inv, X, tr)
+        ref = torch.linalg.solve_triangular(L.T if tr else L, B.double(), upper=tr)
+        assert relerr(X, ref) < 2e-4, (tr, relerr(X, ref))
+
+
 def test_cholesky_flags_non_positive_definite(cuda_ops):
     from sobolev_alignment_b200 import _native as nat
 
