@@ -169,6 +169,72 @@ def test_kmv_accumulates_and_is_linear(cuda_ops):
     assert relerr(o1[:512], K.double() @ V1.double()) < 1e-5
 
 
+def test_kmv_full_size_properties(cuda_ops):
+    """
+    BASELINE config 3 dimensions (p = 3000, M = 50 000 centres, d = 20, Laplacian sigma = 10 on log10
+    counts) on a 150 001-row shard -- several waves of CTA pairs, ragged last tiles, chunk blocks, both
+    the forward (rows x centres) and the transposed (centres x rows) launch shapes.  Size-independent
+    properties: (1) sampled rows against float64 on the device (north_star tolerance), (2) the adjoint
+    identity  <T, K(X, C) V> = <V, K(C, X) T>  between the two launch shapes, (3) the row-shard sum of
+    the transposed product (what the ranks all-reduce) equals the unsharded product.
+    """
+    from sobolev_alignment_b200.engine import pad_cols
+
+    n, M, p, d = 150_001, 50_000, 3000, 20
+    dev = torch.device("cuda")
+    X = syn.log_counts_torch(n, p, seed=21, device=dev)
+    idx = torch.from_numpy(syn.centre_indices(n, M, seed=5)).to(dev)
+    spec = _spec("laplacian", 10.0)
+    C = X[idx]
+    frame = cuda_ops.make_frame(C, spec)
+    Cp, Xp = cuda_ops.prepare(C, frame), cuda_ops.prepare(X, frame)
+    g = torch.Generator(device=dev).manual_seed(9)
+    dp = pad_cols(d)
+    V = torch.zeros(M, dp, device=dev)
+    V[:, :d] = torch.randn(M, d, device=dev, generator=g)
+    T = torch.zeros(n, dp, device=dev)
+    T[:, :d] = torch.randn(n, d, device=dev, generator=g)
+    fwd = cuda_ops.zeros(n, dp)
+    cuda_ops.kmv(spec, frame, Xp, Cp, V, fwd)              # K(X, C) V
+    tr = cuda_ops.zeros(M, dp)
+    cuda_ops.kmv(spec, frame, Cp, Xp, T, tr)               # K(C, X) T
+    # (1) float64 reference on sampled rows (direct differences are too large here: fp64 Gram form)
+    Cd = C.double()
+    cn = (Cd * Cd).sum(1)
+    rows = torch.cat([torch.arange(0, 300, device=dev), torch.randint(0, n, (300,), device=dev, generator=g),
+                      torch.arange(n - 200, n, device=dev), idx[:200]])          # incl. rows that ARE centres
+    Xs = X[rows].double()
+    d2 = ((Xs * Xs).sum(1)[:, None] + cn[None, :] - 2.0 * Xs @ Cd.T).clamp_min_(0.0)
+    d2[d2 < 1e-9 * cn.mean()] = 0.0
+    ref = torch.exp(-d2.sqrt() / 10.0) @ V.double()
+    assert relerr(fwd[rows], ref) < KMV_TOL
+    cols = torch.randint(0, M, (256,), device=dev, generator=g)
+    Cs = Cd[cols]
+    acc = torch.zeros(256, dp, dtype=torch.float64, device=dev)
+    for s0 in range(0, n, 32768):
+        Xc = X[s0:s0 + 32768].double()
+        dd = ((Cs * Cs).sum(1)[:, None] + (Xc * Xc).sum(1)[None, :] - 2.0 * Cs @ Xc.T).clamp_min_(0.0)
+        dd[dd < 1e-9 * cn.mean()] = 0.0
+        acc += torch.exp(-dd.sqrt() / 10.0) @ T[s0:s0 + 32768].double()
+    assert relerr(tr[cols], acc) < KMV_TOL
+    # (2) adjoint identity between the two launch shapes
+    lhs = float((T.double() * fwd.double()).sum())
+    rhs = float((V.double() * tr.double()).sum())
+    scale = float(T.double().norm() * fwd.double().norm())
+    assert abs(lhs - rhs) < 1e-5 * scale, (lhs, rhs, scale)
+    # (3) two row shards, summed, reproduce the transposed product (multi-GPU partial sums)
+    from sobolev_alignment_b200 import _native as nat
+    half = 75_000
+    part = cuda_ops.zeros(M, dp)
+    for s0, e0 in ((0, half), (half, n)):
+        npad = nat.round_up(e0 - s0, nat.NORM_PAD)
+        norms = torch.zeros(npad, device=dev)
+        norms[: e0 - s0] = Xp.norms[s0:e0]
+        shard = nat.Prepared(Xp.data[s0:e0], norms, e0 - s0, p)
+        cuda_ops.kmv(spec, frame, Cp, shard, T[s0:e0].contiguous(), part)
+    assert relerr(part, tr.double()) < 1e-5
+
+
 def test_kmv_rejects_bad_arguments(cuda_ops):
     from sobolev_alignment_b200 import _native as nat
 
