@@ -65,6 +65,13 @@ class CudaOps:
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.stage_rows = int(stage_rows)
         self._pinned = None
+        self._side = None
+
+    def staging_stream(self):
+        """Side stream on which host inputs are copied / prepared while the main stream builds the preconditioner."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
 
     # ------------------------------------------------------------------ memory plumbing
     def zeros(self, *shape, dtype=torch.float32):

@@ -161,19 +161,42 @@ class FalkonSolver:
         self.frame = ops.make_frame(C, self.spec)
         self.Cprep = ops.prepare(C, self.frame)
         del C
+        # Host inputs are staged (pinned copy, H2D, fp16 preparation) on a side stream WHILE the main
+        # stream factorises the preconditioner, which only needs the centres.
+        overlap = hasattr(ops, "staging_stream") and not (torch.is_tensor(X) and X.is_cuda)
+        if overlap:
+            main = torch.cuda.current_stream(ops.device)
+            side = ops.staging_stream()
+            side.wait_stream(main)                      # frame / prepared centres are ready
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            ev[0].record(main)
         self.pre = pre = Preconditioner(ops, self.spec, self.frame, self.Cprep, self.penalty, self.pc_eps)
         Mp = pre.Mp
-        ops.synchronize()
-        self.times["preconditioner"] = time.perf_counter() - t0
-
-        t1 = time.perf_counter()
-        self.Xprep = ops.prepare(X, self.frame)
-        Yd = ops.zeros(n, dp)
-        Yd[:, :d] = ops.to_device(Y)
-        ops.synchronize()
-        self.times["stage_inputs"] = time.perf_counter() - t1
+        if overlap:
+            ev[1].record(main)
+            with torch.cuda.stream(side):
+                ev[2].record(side)
+                self.Xprep = ops.prepare(X, self.frame)
+                Yd = ops.zeros(n, dp)
+                Yd[:, :d] = ops.to_device(Y)
+                ev[3].record(side)
+            for t in (self.Xprep.data, self.Xprep.norms, Yd):
+                t.record_stream(main)
+            main.wait_stream(side)
+            self._phase_events = ev
+        else:
+            ops.synchronize()
+            self.times["preconditioner"] = time.perf_counter() - t0
+            t1 = time.perf_counter()
+            self.Xprep = ops.prepare(X, self.frame)
+            Yd = ops.zeros(n, dp)
+            Yd[:, :d] = ops.to_device(Y)
+            ops.synchronize()
+            self.times["stage_inputs"] = time.perf_counter() - t1
 
         t2 = time.perf_counter()
+        if overlap:
+            ev[4].record(main)
         self.t_buf = ops.empty(n, dp)
         self.w1, self.w2 = ops.zeros(Mp, dp), ops.zeros(Mp, dp)
         B = ops.zeros(Mp, dp)
@@ -190,8 +213,18 @@ class FalkonSolver:
         beta = self._conjugate_gradient(B, Mp, dp)
         pre.invA(beta)
         pre.invT(beta)
+        if overlap:
+            self._phase_events[5].record(main)
         ops.synchronize()
-        self.times["cg"] = time.perf_counter() - t2
+        if overlap:
+            ev = self._phase_events
+            self.times["preconditioner"] = ev[0].elapsed_time(ev[1]) * 1e-3
+            self.times["stage_inputs"] = ev[2].elapsed_time(ev[3]) * 1e-3   # concurrent with the preconditioner
+            self.times["staging_overlapped"] = True
+            self.times["cg"] = ev[4].elapsed_time(ev[5]) * 1e-3
+            del self._phase_events
+        else:
+            self.times["cg"] = time.perf_counter() - t2
         self.times["fit"] = time.perf_counter() - t0
         return beta[:M, :d].contiguous()
 
