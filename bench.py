@@ -292,7 +292,8 @@ def main():
         d2h = est2.alpha_.numel() * 4
         e2e = {"value": e2e_ms / 1e3, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "api": "KRRApprox(method='falkon').fit(X_host_pinned, Y_host_pinned)",
-               "stage_inputs_s": est2.solver_stats_["times"].get("stage_inputs")}
+               "stage_inputs_s": est2.solver_stats_["times"].get("stage_inputs"),
+               "phases_s": est2.solver_stats_["times"], "host_overhead_s": e2e_wall / 1e3 - est2.solver_stats_["times"]["fit"]}
 
     if rank != 0:
         if world > 1:
