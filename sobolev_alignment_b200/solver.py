@@ -18,6 +18,7 @@ deterministic, so ranks stay bit-identical without a broadcast.
 
 from __future__ import annotations
 
+import threading
 import time
 
 import torch
@@ -170,16 +171,34 @@ class FalkonSolver:
             side.wait_stream(main)                      # frame / prepared centres are ready
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
             ev[0].record(main)
+            # The preconditioner is ~2000 kernel launches: the enqueueing thread blocks on the launch
+            # queue for most of its GPU time, so the staging loop runs on a helper thread (CUDA calls
+            # release the GIL) instead of behind it.
+            staged = {}
+
+            def _stage():
+                try:
+                    torch.cuda.set_device(ops.device)
+                    with torch.cuda.stream(side):
+                        ev[2].record(side)
+                        staged["X"] = ops.prepare(X, self.frame)
+                        yd = ops.zeros(n, dp)
+                        yd[:, :d] = ops.to_device(Y)
+                        staged["Y"] = yd
+                        ev[3].record(side)
+                except BaseException as exc:  # noqa: BLE001 - re-raised on the calling thread
+                    staged["error"] = exc
+
+            helper = threading.Thread(target=_stage, name="sobolev-b200-staging")
+            helper.start()
         self.pre = pre = Preconditioner(ops, self.spec, self.frame, self.Cprep, self.penalty, self.pc_eps)
         Mp = pre.Mp
         if overlap:
             ev[1].record(main)
-            with torch.cuda.stream(side):
-                ev[2].record(side)
-                self.Xprep = ops.prepare(X, self.frame)
-                Yd = ops.zeros(n, dp)
-                Yd[:, :d] = ops.to_device(Y)
-                ev[3].record(side)
+            helper.join()
+            if "error" in staged:
+                raise staged["error"]
+            self.Xprep, Yd = staged["X"], staged["Y"]
             for t in (self.Xprep.data, self.Xprep.norms, Yd):
                 t.record_stream(main)
             main.wait_stream(side)
