@@ -119,6 +119,18 @@ int sa_trsm(void* stream, const float* L, int64_t M, int64_t ldl, const float* i
             int dp, int transpose, void* workspace, int64_t workspace_bytes);
 
 /*
+ * Two dependent solves in one launch (the preconditioner is always applied as such a pair: A^-1 then
+ * T^-1, and T^-T then A^-T, `FalkonPreconditioner.apply / apply_t` [ext]):
+ *   Xa <- op(La)^-1 Xa                       (in place)
+ *   Xb <- op(Lb)^-1 (Xa + lambda * V)        (V may be NULL)
+ * op = identity (transpose = 0) or transposition (1) for both.  The second chain starts block c as soon
+ * as the first has published it, so the pair costs one chain latency.  Xa != Xb; same workspace contract.
+ */
+int sa_trsm_pair(void* stream, const float* La, int64_t lda, const float* inva, const float* Lb,
+                 int64_t ldb, const float* invb, int64_t M, float* Xa, float* Xb, const float* V,
+                 float lambda, int dp, int transpose, void* workspace, int64_t workspace_bytes);
+
+/*
  * Conjugate-gradient vector kernels (falkon `ConjugateGradient.solve` [ext]); all M x dp fp32.
  * sa_coldot:   out[c] = sum_i P[i, c] * Q[i, c]                    (out is overwritten)
  * sa_cg_update: alpha_c = rs_old[c] / (pAp[c] + eps);  X += P alpha;  R -= AP alpha (if AP != NULL);

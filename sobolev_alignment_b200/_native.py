@@ -78,6 +78,8 @@ _SIGNATURES = {
     "sa_add_diag": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float]),
     "sa_trsm_workspace_bytes": (c_int64, [c_int64]),
     "sa_trsm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64]),
+    "sa_trsm_pair": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                             c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int64]),
     "sa_coldot": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "sa_cg_update": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_float, c_void_p]),
@@ -290,6 +292,35 @@ def trsm(L: torch.Tensor, invdiag: torch.Tensor, B: torch.Tensor, transpose: boo
         STATS.trsm_events.append((m * (m + TILE) / 2 * 4.0, ev[0], ev[1]))   # the triangle is read once
     STATS.launches += 1
     return B
+
+
+def trsm_pair(La: torch.Tensor, inva: torch.Tensor, Lb: torch.Tensor, invb: torch.Tensor, Xa: torch.Tensor,
+              Xb: torch.Tensor, V: torch.Tensor | None, lam: float, transpose: bool):
+    """Xa <- op(La)^-1 Xa ;  Xb <- op(Lb)^-1 (Xa + lam V)   -- two pipelined chained solves in one launch."""
+    _req(La, torch.float32, "La")
+    _req(Lb, torch.float32, "Lb")
+    _req(Xa, torch.float32, "Xa")
+    _req(Xb, torch.float32, "Xb")
+    if V is not None:
+        _req(V, torch.float32, "V")
+    m = La.shape[0]
+    if Lb.shape[0] != m or Xa.shape != Xb.shape or Xa.shape[0] != m or (V is not None and V.shape != Xa.shape):
+        raise ValueError("shape mismatch")
+    if Xa.data_ptr() == Xb.data_ptr():
+        raise ValueError("Xa and Xb must be different buffers")
+    ev = None
+    if STATS.time_kmv:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    ws = _workspace(Xa.device, int(load().sa_trsm_workspace_bytes(m)))
+    _check(load().sa_trsm_pair(_stream(), La.data_ptr(), La.stride(0), inva.data_ptr(), Lb.data_ptr(), Lb.stride(0),
+                               invb.data_ptr(), m, Xa.data_ptr(), Xb.data_ptr(), _ptr(V), float(lam), Xa.shape[1],
+                               int(transpose), ws.data_ptr(), ws.numel()))
+    if ev is not None:
+        ev[1].record()
+        STATS.trsm_events.append((2 * m * (m + TILE) / 2 * 4.0, ev[0], ev[1]))   # both triangles are read once
+    STATS.launches += 1
+    return Xb
 
 
 def coldot(P: torch.Tensor, Q: torch.Tensor, out: torch.Tensor):

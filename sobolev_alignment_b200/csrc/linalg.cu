@@ -567,10 +567,27 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// One solve, or two pipelined ones: job 1 solves  op(L1) x1 = x0 + lambda V  where x0 is job 0's
+// solution.  Both chains run in the same block order, so block c of job 1 starts as soon as job 0 has
+// published block c: the pair costs one chain latency instead of two (the FALKON operator applies
+// A^-1 then T^-1, and T^-T then A^-T, back to back).
+struct TrsmJob {
+  const float* L;
+  long long ldl;
+  const float* invdiag;
+  const float* rhs;  // job 0: == x (in place); job 1: job 0's x
+  float* x;          // solution, M x DP
+  const float* V;    // optional additive term of the rhs (NULL = none)
+  float lambda;
+};
+struct TrsmJobs {
+  TrsmJob job[2];
+  int njobs;
+};
+
 template <int DP, bool TRANS>
 __global__ void __launch_bounds__(256)
-trsm_chain_kernel(const float* __restrict__ L, long long ldl, const float* __restrict__ invdiag,
-                  float* __restrict__ Bm, int nblk, int* __restrict__ sync) {
+trsm_chain_kernel(const TrsmJobs jobs, int nblk, int* __restrict__ sync) {
   constexpr int NB8 = (DP + 7) / 8;
   constexpr int LT = trsm_ldt(TRANS);
   constexpr int LX = trsm_ldx(NB8);
@@ -580,9 +597,15 @@ trsm_chain_kernel(const float* __restrict__ L, long long ldl, const float* __res
   __shared__ int s_ticket, s_next;
   if (threadIdx.x == 0) s_ticket = atomicAdd(sync, 1);
   __syncthreads();
-  const int c = s_ticket;             // c blocks are solved before this one
+  const int jid = s_ticket % jobs.njobs;  // tickets alternate between the jobs: both chains advance together
+  const int c = s_ticket / jobs.njobs;    // c blocks of this job are solved before this one
+  const TrsmJob& J = jobs.job[jid];
+  const float* __restrict__ L = J.L;
+  const long long ldl = J.ldl;
+  const float* __restrict__ invdiag = J.invdiag;
+  float* __restrict__ Bm = J.x;
   const int blk = TRANS ? nblk - 1 - c : c;
-  int* flags = sync + 64;
+  int* flags = sync + 64 + jid * nblk;
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int m0 = (threadIdx.x >> 5) * 16;
@@ -613,17 +636,43 @@ trsm_chain_kernel(const float* __restrict__ L, long long ldl, const float* __res
   issue_tile(0);
   cp_async_commit();
 
+  auto wait_flag = [&](const int* f, int what) {  // bounded spin: a bug must trap, not hang the GPU
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    while (ld_acquire_gpu(f) == 0) {
+      if ((++spins & 0x3FFu) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000ull) {
+          printf("sobolev_b200: trsm chain timed out waiting for block %d (job %d cta %d)\n", what, jid, c);
+          __trap();
+        }
+      }
+    }
+  };
   // this thread's fragment of the block of b: rows m0+g and m0+g+8, columns nb*8 + 2t, +1
-  float* b0 = Bm + (static_cast<long long>(blk) * TS + m0 + g) * DP;
+  const long long frow = static_cast<long long>(blk) * TS + m0 + g;
+  float* b0 = Bm + frow * DP;
   float* b1 = b0 + 8 * DP;
+  if (jid == 1) {  // the rhs is job 0's solution of the same block
+    if (threadIdx.x == 0) wait_flag(sync + 64 + blk, blk);
+    __syncthreads();
+  }
   float bfrag[NB8][4];
 #pragma unroll
   for (int nb = 0; nb < NB8; ++nb) {
     const int cc = nb * 8 + 2 * t;
     float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
     if (cc < DP) {
-      v0 = *reinterpret_cast<const float2*>(b0 + cc);
-      v1 = *reinterpret_cast<const float2*>(b1 + cc);
+      v0 = __ldcg(reinterpret_cast<const float2*>(J.rhs + frow * DP + cc));
+      v1 = __ldcg(reinterpret_cast<const float2*>(J.rhs + (frow + 8) * DP + cc));
+      if (J.V != nullptr) {
+        const float2 a0 = *reinterpret_cast<const float2*>(J.V + frow * DP + cc);
+        const float2 a1 = *reinterpret_cast<const float2*>(J.V + (frow + 8) * DP + cc);
+        v0.x = fmaf(J.lambda, a0.x, v0.x); v0.y = fmaf(J.lambda, a0.y, v0.y);
+        v1.x = fmaf(J.lambda, a1.x, v1.x); v1.y = fmaf(J.lambda, a1.y, v1.y);
+      }
     }
     bfrag[nb][0] = v0.x; bfrag[nb][1] = v0.y; bfrag[nb][2] = v1.x; bfrag[nb][3] = v1.y;
   }
@@ -631,22 +680,7 @@ trsm_chain_kernel(const float* __restrict__ L, long long ldl, const float* __res
   bool have_x = false;  // x of the current dependency was prefetched by the previous iteration
   for (int d = 0; d < c; ++d) {
     if (threadIdx.x == 0) {
-      if (!have_x) {
-        const int* f = flags + src_of(d);
-        unsigned spins = 0;
-        unsigned long long t0 = 0;
-        while (ld_acquire_gpu(f) == 0) {
-          if ((++spins & 0x3FFu) == 0) {
-            unsigned long long now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ull) {
-              printf("sobolev_b200: trsm chain timed out waiting for block %d (cta %d)\n", src_of(d), c);
-              __trap();
-            }
-          }
-        }
-      }
+      if (!have_x) wait_flag(flags + src_of(d), src_of(d));
       s_next = (d + 1 < c) ? ld_acquire_gpu(flags + src_of(d + 1)) : 0;
     }
     __syncthreads();  // x_src is published; everyone is done with slot (d + 1) & 1 of both rings
@@ -919,26 +953,34 @@ static int red_grid(long long M, int rows_per_block) {
 }
 
 template <int DP>
+static int trsm_chain_launch(cudaStream_t st, const TrsmJobs& jobs, long long M, int transpose, int* sync) {
+  const int nblk = static_cast<int>(M / TS);
+  // workspace: [0] ticket counter (64 ints reserved), then one flag per block and job
+  const int smem = (2 * TS * trsm_ldt(transpose != 0) + 2 * TS * trsm_ldx((DP + 7) / 8)) * static_cast<int>(sizeof(float));
+  SAB_CHECK_CUDA(cudaMemsetAsync(sync, 0, (64 + 2 * nblk) * sizeof(int), st));
+  if (transpose) {
+    auto kern = trsm_chain_kernel<DP, true>;
+    SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<nblk * jobs.njobs, 256, smem, st>>>(jobs, nblk, sync);
+  } else {
+    auto kern = trsm_chain_kernel<DP, false>;
+    SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<nblk * jobs.njobs, 256, smem, st>>>(jobs, nblk, sync);
+  }
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int DP>
 static int trsm_launch(cudaStream_t st, const float* L, long long M, long long ldl, const float* invdiag,
                        float* B, int transpose, int* sync) {
   const int nblk = static_cast<int>(M / TS);
   const char* ev = std::getenv("SAB_TRSM_STEPS");
   if (sync != nullptr && !(ev && std::atoi(ev) != 0)) {
-    // one launch: dependency chain through flags in `sync` ([0] ticket counter, [1 + i] block i solved)
-    // workspace: [0] ticket counter (64 ints reserved), then one flag per block
-    const int smem = (2 * TS * trsm_ldt(transpose != 0) + 2 * TS * trsm_ldx((DP + 7) / 8)) * static_cast<int>(sizeof(float));
-    SAB_CHECK_CUDA(cudaMemsetAsync(sync, 0, (64 + nblk) * sizeof(int), st));
-    if (transpose) {
-      auto kern = trsm_chain_kernel<DP, true>;
-      SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      kern<<<nblk, 256, smem, st>>>(L, ldl, invdiag, B, nblk, sync);
-    } else {
-      auto kern = trsm_chain_kernel<DP, false>;
-      SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      kern<<<nblk, 256, smem, st>>>(L, ldl, invdiag, B, nblk, sync);
-    }
-    SAB_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    TrsmJobs jobs = {};
+    jobs.njobs = 1;
+    jobs.job[0] = TrsmJob{L, ldl, invdiag, B, B, nullptr, 0.f};
+    return trsm_chain_launch<DP>(st, jobs, M, transpose, sync);
   }
   const int smem = (TS * trsm_ldt(transpose != 0) + TS * trsm_ldx((DP + 7) / 8)) * static_cast<int>(sizeof(float));
   cudaLaunchConfig_t cfg = {};
@@ -1135,7 +1177,41 @@ extern "C" int sa_add_diag(void* stream, float* A, int64_t M, int64_t lda, float
   return 0;
 }
 
-extern "C" int64_t sa_trsm_workspace_bytes(int64_t M) { return M <= 0 ? -1 : (64 + M / TS + 1) * 4; }
+extern "C" int64_t sa_trsm_workspace_bytes(int64_t M) { return M <= 0 ? -1 : (64 + 2 * (M / TS) + 2) * 4; }
+
+template <int DP>
+static int trsm_pair_dp(cudaStream_t st, const TrsmJobs& jobs, long long M, int transpose, int* sync) {
+  return trsm_chain_launch<DP>(st, jobs, M, transpose, sync);
+}
+
+extern "C" int sa_trsm_pair(void* stream, const float* La, int64_t lda, const float* inva, const float* Lb,
+                            int64_t ldb, const float* invb, int64_t M, float* Xa, float* Xb, const float* V,
+                            float lambda, int dp, int transpose, void* workspace, int64_t workspace_bytes) {
+  SAB_REQUIRE_MAT(M, lda, La);
+  SAB_REQUIRE_MAT(M, ldb, Lb);
+  SAB_REQUIRE(inva != nullptr && invb != nullptr && Xa != nullptr && Xb != nullptr && Xa != Xb, "bad operands");
+  SAB_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 &&
+                  workspace_bytes >= sa_trsm_workspace_bytes(M),
+              "workspace must hold sa_trsm_workspace_bytes(M) = %lld bytes", (long long)sa_trsm_workspace_bytes(M));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TrsmJobs jobs = {};
+  jobs.njobs = 2;
+  jobs.job[0] = TrsmJob{La, lda, inva, Xa, Xa, nullptr, 0.f};
+  jobs.job[1] = TrsmJob{Lb, ldb, invb, Xa, Xb, V, lambda};
+  int* sync = static_cast<int*>(workspace);
+  switch (dp) {
+    case 4: return trsm_pair_dp<4>(st, jobs, M, transpose, sync);
+    case 8: return trsm_pair_dp<8>(st, jobs, M, transpose, sync);
+    case 12: return trsm_pair_dp<12>(st, jobs, M, transpose, sync);
+    case 16: return trsm_pair_dp<16>(st, jobs, M, transpose, sync);
+    case 20: return trsm_pair_dp<20>(st, jobs, M, transpose, sync);
+    case 24: return trsm_pair_dp<24>(st, jobs, M, transpose, sync);
+    case 28: return trsm_pair_dp<28>(st, jobs, M, transpose, sync);
+    case 32: return trsm_pair_dp<32>(st, jobs, M, transpose, sync);
+  }
+  set_error("dp must be a multiple of 4 in [4, 32], got %d", dp);
+  return 2;
+}
 
 extern "C" int sa_trsm(void* stream, const float* L, int64_t M, int64_t ldl, const float* invdiag,
                        float* B, int dp, int transpose, void* workspace, int64_t workspace_bytes) {

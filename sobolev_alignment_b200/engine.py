@@ -151,6 +151,7 @@ class CudaOps:
     ltl = staticmethod(nat.ltl)
     add_diag = staticmethod(nat.add_diag)
     trsm = staticmethod(nat.trsm)
+    trsm_pair = staticmethod(nat.trsm_pair)
     coldot = staticmethod(nat.coldot)
     cg_update = staticmethod(nat.cg_update)
     cg_direction = staticmethod(nat.cg_direction)

@@ -102,6 +102,27 @@ class Preconditioner:
     def invAt(self, v):
         return self.ops.trsm(self.LA, self.LA_inv, v, False)
 
+    # the operator always applies the factors in pairs; one pipelined launch when the engine has it
+    def invA_invT(self, v, z):
+        """v <- A^-1 v (in place);  z <- T^-1 v."""
+        pair = getattr(self.ops, "trsm_pair", None)
+        if pair is not None:
+            return pair(self.LA, self.LA_inv, self.L, self.L_inv, v, z, None, 0.0, True)
+        self.invA(v)
+        z.copy_(v)
+        return self.invT(z)
+
+    def invTt_invAt(self, w, out, v=None, lam=0.0):
+        """w <- T^-T w (in place);  out <- A^-T (w + lam v)."""
+        pair = getattr(self.ops, "trsm_pair", None)
+        if pair is not None:
+            return pair(self.L, self.L_inv, self.LA, self.LA_inv, w, out, v, lam, False)
+        self.invTt(w)
+        out.copy_(w)
+        if v is not None:
+            self.ops.axpby(lam, v, 1.0, out)
+        return self.invAt(out)
+
 
 class FalkonSolver:
     def __init__(self, ops, spec: KernelSpec, penalty: float, maxiter: int = 20, pc_eps: float = 1e-5,
@@ -131,17 +152,12 @@ class FalkonSolver:
     def _bhb(self, u, out):
         """out = BHB u  (u is left untouched; w1/w2 are scratch)."""
         ops, pre = self.ops, self.pre
-        v = self.w1
+        v, z, w = self.w1, self.w2, self.w3
         v.copy_(u)
-        pre.invA(v)                       # v = A^-1 u
-        z = self.w2
-        z.copy_(v)
-        pre.invT(z)                       # z = T^-1 v
-        self._knm_t_knm(z, out)           # out = K_nM^T K_nM z
-        ops.axpby(1.0 / self.n_total, out, 0.0, out)   # out /= n
-        pre.invTt(out)                    # T^-T (. / n)
-        ops.axpby(self.penalty, v, 1.0, out)  # + lambda v
-        pre.invAt(out)
+        pre.invA_invT(v, z)               # v = A^-1 u ; z = T^-1 v
+        self._knm_t_knm(z, w)             # w = K_nM^T K_nM z
+        ops.axpby(1.0 / self.n_total, w, 0.0, w)   # w /= n
+        pre.invTt_invAt(w, out, v, self.penalty)    # out = A^-T (T^-T w + lambda v)
         return out
 
     # ------------------------------------------------------------------ fit
@@ -217,21 +233,23 @@ class FalkonSolver:
         if overlap:
             ev[4].record(main)
         self.t_buf = ops.empty(n, dp)
-        self.w1, self.w2 = ops.zeros(Mp, dp), ops.zeros(Mp, dp)
+        self.w1, self.w2, self.w3 = ops.zeros(Mp, dp), ops.zeros(Mp, dp), ops.zeros(Mp, dp)
         B = ops.zeros(Mp, dp)
+        Bw = self.w3
         # rhs = A^-T T^-T K_nM^T (Y / n)
         ops.axpby(1.0 / self.n_total, Yd, 0.0, Yd)     # Y / n
-        ops.kmv(self.spec, self.frame, self.Cprep, self.Xprep, Yd, B[:M])
+        Bw.zero_()
+        ops.kmv(self.spec, self.frame, self.Cprep, self.Xprep, Yd, Bw[:M])
         self.n_kmv_ += 1
-        self.comm.all_reduce(B)
+        self.comm.all_reduce(Bw)
         del Yd
-        pre.invTt(B)
-        pre.invAt(B)
+        pre.invTt_invAt(Bw, B)            # B = A^-T T^-T K_nM^T (Y / n)
         pre.check()
 
         beta = self._conjugate_gradient(B, Mp, dp)
-        pre.invA(beta)
-        pre.invT(beta)
+        alpha = self.w2
+        pre.invA_invT(beta, alpha)        # alpha = T^-1 A^-1 beta
+        beta = alpha
         if overlap:
             self._phase_events[5].record(main)
         ops.synchronize()
@@ -280,7 +298,7 @@ class FalkonSolver:
 
     # ------------------------------------------------------------------ release
     def release(self):
-        for name in ("pre", "Xprep", "t_buf", "w1", "w2"):
+        for name in ("pre", "Xprep", "t_buf", "w1", "w2", "w3"):
             if hasattr(self, name):
                 delattr(self, name)
 

@@ -325,6 +325,37 @@ def test_cholesky_ltl_trsm(cuda_ops, M, dp, nb, monkeypatch):
         assert relerr(X, ref) < 5e-5
 
 
+@pytest.mark.parametrize("M,dp", [(128, 4), (1024, 20), (4096, 12)])
+def test_paired_solves_match_two_single_solves(cuda_ops, M, dp):
+    """sa_trsm_pair (two pipelined chains in one launch) against two sa_trsm calls, both directions, with the lambda V term."""
+    from sobolev_alignment_b200 import _native as nat
+
+    g = torch.Generator(device="cuda").manual_seed(M)
+    facs = []
+    for scale in (6.0, 9.0):
+        Z = torch.randn(M, 16, device="cuda", generator=g)
+        A = torch.cdist(Z, Z).mul_(-1.0 / scale).exp_()
+        A.diagonal().add_(0.05)
+        inv = torch.empty(M // 128, 128, 128, device="cuda")
+        info = torch.zeros(1, dtype=torch.int32, device="cuda")
+        nat.potrf(A, inv, info)
+        assert int(info) == 0
+        facs.append((A, inv))
+    (La, ia), (Lb, ib) = facs
+    B = torch.randn(M, dp, device="cuda", generator=g)
+    V = torch.randn(M, dp, device="cuda", generator=g)
+    for tr in (False, True):
+        for lam, Vt in ((0.0, None), (0.37, V)):
+            xa = B.clone()
+            nat.trsm(La, ia, xa, tr)
+            xb = xa.clone() if Vt is None else (xa + lam * Vt)
+            nat.trsm(Lb, ib, xb, tr)
+            pa, pb = B.clone(), torch.full_like(B, float("nan"))
+            nat.trsm_pair(La, ia, Lb, ib, pa, pb, Vt, lam, tr)
+            assert torch.equal(pa, xa)                 # same arithmetic, same order: bit identical
+            assert relerr(pb, xb.double()) < 1e-6
+
+
 def test_large_factorisation_and_chained_solves(cuda_ops):
     """
     M = 24 576 = 192 blocks: more CTAs than SMs in the single-launch triangular solve (late blocks start
