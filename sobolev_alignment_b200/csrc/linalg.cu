@@ -655,27 +655,33 @@ trsm_chain_kernel(const TrsmJobs jobs, int nblk, int* __restrict__ sync) {
   const long long frow = static_cast<long long>(blk) * TS + m0 + g;
   float* b0 = Bm + frow * DP;
   float* b1 = b0 + 8 * DP;
-  if (jid == 1) {  // the rhs is job 0's solution of the same block
-    if (threadIdx.x == 0) wait_flag(sync + 64 + blk, blk);
-    __syncthreads();
-  }
+  // bfrag accumulates  rhs - sum_k L(blk, k) x_k.  Job 0 reads its rhs right away; job 1's rhs is job 0's
+  // solution of the same block, the LAST thing it needs: it is fetched after the elimination loop, so
+  // the second chain trails the first by one step instead of serialising behind it.
   float bfrag[NB8][4];
+  auto load_rhs = [&]() {
 #pragma unroll
-  for (int nb = 0; nb < NB8; ++nb) {
-    const int cc = nb * 8 + 2 * t;
-    float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
-    if (cc < DP) {
-      v0 = __ldcg(reinterpret_cast<const float2*>(J.rhs + frow * DP + cc));
-      v1 = __ldcg(reinterpret_cast<const float2*>(J.rhs + (frow + 8) * DP + cc));
-      if (J.V != nullptr) {
-        const float2 a0 = *reinterpret_cast<const float2*>(J.V + frow * DP + cc);
-        const float2 a1 = *reinterpret_cast<const float2*>(J.V + (frow + 8) * DP + cc);
-        v0.x = fmaf(J.lambda, a0.x, v0.x); v0.y = fmaf(J.lambda, a0.y, v0.y);
-        v1.x = fmaf(J.lambda, a1.x, v1.x); v1.y = fmaf(J.lambda, a1.y, v1.y);
+    for (int nb = 0; nb < NB8; ++nb) {
+      const int cc = nb * 8 + 2 * t;
+      float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+      if (cc < DP) {
+        v0 = __ldcg(reinterpret_cast<const float2*>(J.rhs + frow * DP + cc));
+        v1 = __ldcg(reinterpret_cast<const float2*>(J.rhs + (frow + 8) * DP + cc));
+        if (J.V != nullptr) {
+          const float2 a0 = *reinterpret_cast<const float2*>(J.V + frow * DP + cc);
+          const float2 a1 = *reinterpret_cast<const float2*>(J.V + (frow + 8) * DP + cc);
+          v0.x = fmaf(J.lambda, a0.x, v0.x); v0.y = fmaf(J.lambda, a0.y, v0.y);
+          v1.x = fmaf(J.lambda, a1.x, v1.x); v1.y = fmaf(J.lambda, a1.y, v1.y);
+        }
       }
+      bfrag[nb][0] += v0.x; bfrag[nb][1] += v0.y; bfrag[nb][2] += v1.x; bfrag[nb][3] += v1.y;
     }
-    bfrag[nb][0] = v0.x; bfrag[nb][1] = v0.y; bfrag[nb][2] = v1.x; bfrag[nb][3] = v1.y;
-  }
+  };
+#pragma unroll
+  for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bfrag[nb][i] = 0.f;
+  if (jid == 0) load_rhs();
 
   bool have_x = false;  // x of the current dependency was prefetched by the previous iteration
   for (int d = 0; d < c; ++d) {
@@ -701,6 +707,11 @@ trsm_chain_kernel(const TrsmJobs jobs, int nblk, int* __restrict__ sync) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) bfrag[nb][i] -= acc[nb][i];
     have_x = nxt;
+  }
+  if (jid == 1) {
+    if (threadIdx.x == 0) wait_flag(sync + 64 + blk, blk);  // job 0 has published this block
+    __syncthreads();
+    load_rhs();
   }
   cp_async_wait<0>();
   __syncthreads();  // inverted diagonal block landed; x ring free

@@ -17,3 +17,14 @@ for tr in (False, True, False, True):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); nat.trsm(A, invd, B, tr); e1.record(); torch.cuda.synchronize()
     print(f"trsm trans={tr}: {e0.elapsed_time(e1):.3f} ms ({M // 128} steps, {e0.elapsed_time(e1) * 1e3 / (M // 128):.1f} us/step)")
+
+# paired solves (two pipelined chains in one launch)
+G = (torch.exp(-torch.cdist(Z, Z) / 5.0) + 1e-2 * torch.eye(M, device=dev)).contiguous()
+invg = torch.empty(M // 128, 128, 128, device=dev)
+nat.potrf(G, invg, info)
+Xa, Xb = torch.randn(M, 20, device=dev), torch.empty(M, 20, device=dev)
+torch.cuda.synchronize()
+for tr in (False, True, False, True):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); nat.trsm_pair(A, invd, G, invg, Xa, Xb, None, 0.0, tr); e1.record(); torch.cuda.synchronize()
+    print(f"trsm_pair trans={tr}: {e0.elapsed_time(e1):.3f} ms")
