@@ -65,6 +65,7 @@ class CudaOps:
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.stage_rows = int(stage_rows)
         self._pinned = None
+        self._pinned_events = [None, None]   # last device-side use of each pinned staging buffer
         self._side = None
 
     def staging_stream(self):
@@ -119,15 +120,21 @@ class CudaOps:
             return out
         rows = max(1, min(self.stage_rows, n))
         if self._pinned is None or self._pinned[0].shape[1] != p or self._pinned[0].shape[0] < rows:
+            for ev in self._pinned_events:
+                if ev is not None:
+                    ev.synchronize()     # copies out of the old buffers are done before they are dropped
             self._pinned = [torch.empty(rows, p, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._pinned_events = [None, None]
         dev_bufs = [torch.empty(rows, p, dtype=torch.float32, device=self.device) for _ in range(2)]
-        events = [None, None]
+        # The events outlive this call: the NEXT prepare() must not overwrite a pinned buffer whose
+        # asynchronous H2D copy (enqueued by this call) is still in flight.
+        events = self._pinned_events
         stream = torch.cuda.current_stream(self.device)
         for i, s in enumerate(range(0, n, rows)):
             e = min(n, s + rows)
             b = i & 1
             if events[b] is not None:
-                events[b].synchronize()  # the pinned buffer is free again
+                events[b].synchronize()  # the pinned buffer (and device buffer b) is free again
             src = X[s:e]
             if src.is_pinned() and src.dtype == torch.float32 and src.is_contiguous():
                 dev_bufs[b][: e - s].copy_(src, non_blocking=True)

@@ -99,6 +99,26 @@ def test_prepare_chunked_staging_equals_single_shot(cuda_ops):
     assert torch.equal(P.data, Q.data) and torch.equal(P.norms, Q.norms)
 
 
+def test_prepare_back_to_back_host_inputs(cuda_ops):
+    """
+    Regression: two prepare() calls on pageable host tensors in a row.  The second call must not reuse a
+    pinned staging buffer while the first call's asynchronous H2D copy out of it is still in flight
+    (seen once as a 24 % error of an otherwise deterministic product).
+    """
+    spec = _spec("laplacian", 3.0)
+    g = torch.Generator().manual_seed(11)
+    big = torch.randn(60000, 1000, generator=g)
+    small = torch.randn(700, 1000, generator=g) + 5.0
+    frame = cuda_ops.make_frame(small, spec)
+    for _ in range(3):
+        Pb = cuda_ops.prepare(big, frame)
+        Ps = cuda_ops.prepare(small, frame)      # overwrites the pinned buffers right away
+        ref_b = cuda_ops.prepare(big.cuda(), frame)
+        ref_s = cuda_ops.prepare(small.cuda(), frame)
+        assert torch.equal(Pb.data, ref_b.data) and torch.equal(Pb.norms, ref_b.norms)
+        assert torch.equal(Ps.data, ref_s.data) and torch.equal(Ps.norms, ref_s.norms)
+
+
 # ---------------------------------------------------------------------------- fused kmv
 @pytest.mark.parametrize("family,okernel,nu", FAMILIES)
 @pytest.mark.parametrize("a,b,p,d", [(1, 1, 1, 1), (128, 256, 64, 4), (300, 500, 100, 7), (2000, 500, 500, 10),
