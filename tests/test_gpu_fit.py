@@ -171,3 +171,63 @@ def test_alignment_golden(tag, kernel, params):
     Cs, Ct = Xs[g["idx_s"]], Xt[g["idx_t"]]
     assert relerr(gram(tgt.kernel_, Cs, a_s, Ct, a_t), g[f"{tag}_M_XY"]) < 2e-4
     assert relerr(gram(src.kernel_, Cs, a_s, Cs, a_s), g[f"{tag}_M_X"]) < 2e-4
+
+
+# ---------------------------------------------------------------------------- row-sharded fit on the real engine
+def _sharded_rank_main(rank, world, port, out_dir):
+    import os
+
+    import torch.distributed as dist
+
+    from sobolev_alignment_b200.falkon import Falkon, FalkonOptions
+    from sobolev_alignment_b200.falkon.kernels import LaplacianKernel
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    # both ranks share cuda:0 (NCCL refuses two ranks on one device); gloo all-reduces the CUDA tensors
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(0)
+        Xall = syn.log_counts_numpy(3001 + 40, 300, seed=4)
+        Y = torch.from_numpy(syn.targets_numpy(Xall, 5, seed=6)[:3001])
+        X, Xv = torch.from_numpy(Xall[:3001]), torch.from_numpy(Xall[3001:])
+        bounds = np.linspace(0, X.shape[0], world + 1).astype(int)
+        Xl, Yl = X[bounds[rank]:bounds[rank + 1]], Y[bounds[rank]:bounds[rank + 1]]
+        clf = Falkon(kernel=LaplacianKernel(sigma=9.0), penalty=1e-4, M=400, seed=5,
+                     options=FalkonOptions(row_sharded=True))
+        clf.fit(Xl, Yl)
+        pred = clf.predict(Xv)
+        torch.save({"alpha": clf.alpha_.cpu(), "centres": clf.ny_points_.cpu(), "pred": pred.cpu(),
+                    "n_total": clf.solver_stats_["n_total"]}, os.path.join(out_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_fit_on_gpu_world2(tmp_path):
+    """
+    The multi-GPU path (row shards, centre exchange, all-reduce of the M x d partial sums per product pair)
+    on the CUDA engine: two ranks on this one GPU over gloo.  Ranks must stay bit-identical and agree with
+    the float64 oracle of the unsharded problem.
+    """
+    import os
+    import socket
+
+    import torch.multiprocessing as mp
+
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    mp.spawn(_sharded_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(os.path.join(tmp_path, "rank0.pt"))
+    r1 = torch.load(os.path.join(tmp_path, "rank1.pt"))
+    assert r0["n_total"] == 3001
+    assert torch.equal(r0["alpha"], r1["alpha"]) and torch.equal(r0["centres"], r1["centres"])
+    Xall = syn.log_counts_numpy(3001 + 40, 300, seed=4)
+    Y = torch.from_numpy(syn.targets_numpy(Xall, 5, seed=6)[:3001])
+    X, Xv = torch.from_numpy(Xall[:3001]), torch.from_numpy(Xall[3001:])
+    idx = np.sort(np.random.default_rng(5).choice(3001, size=400, replace=False))
+    assert torch.equal(r0["centres"], X[idx])
+    ref = fo.falkon_fit(X, Y, X[idx], "laplacian", 9.0, 1e-4)
+    refp = fo.falkon_predict(Xv, X[idx], ref, "laplacian", 9.0)
+    assert relerr(r0["pred"], refp) < PRED_TOL
