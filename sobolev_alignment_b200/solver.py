@@ -26,6 +26,7 @@ import torch
 from .engine import KernelSpec, pad_cols
 
 TILE = 128
+MAX_COLS = 32   # right-hand-side columns per CG run / fused-kernel launch
 
 
 class Comm:
@@ -169,9 +170,6 @@ class FalkonSolver:
         ops = self.ops
         t0 = time.perf_counter()
         n, d = Y.shape
-        dp = pad_cols(d)
-        if dp > 32:
-            raise NotImplementedError("more than 32 output columns: split Y column-wise")
         self.n_total = int(n_total) if n_total is not None else self.comm.sum_int(n, ops.device)
         C = ops.to_device(centres)
         M = self.M = C.shape[0]
@@ -198,9 +196,7 @@ class FalkonSolver:
                     with torch.cuda.stream(side):
                         ev[2].record(side)
                         staged["X"] = ops.prepare(X, self.frame)
-                        yd = ops.zeros(n, dp)
-                        yd[:, :d] = ops.to_device(Y)
-                        staged["Y"] = yd
+                        staged["Y"] = ops.to_device(Y)
                         ev[3].record(side)
                 except BaseException as exc:  # noqa: BLE001 - re-raised on the calling thread
                     staged["error"] = exc
@@ -214,8 +210,8 @@ class FalkonSolver:
             helper.join()
             if "error" in staged:
                 raise staged["error"]
-            self.Xprep, Yd = staged["X"], staged["Y"]
-            for t in (self.Xprep.data, self.Xprep.norms, Yd):
+            self.Xprep, Yfull = staged["X"], staged["Y"]
+            for t in (self.Xprep.data, self.Xprep.norms, Yfull):
                 t.record_stream(main)
             main.wait_stream(side)
             self._phase_events = ev
@@ -224,32 +220,30 @@ class FalkonSolver:
             self.times["preconditioner"] = time.perf_counter() - t0
             t1 = time.perf_counter()
             self.Xprep = ops.prepare(X, self.frame)
-            Yd = ops.zeros(n, dp)
-            Yd[:, :d] = ops.to_device(Y)
+            Yfull = ops.to_device(Y)
             ops.synchronize()
             self.times["stage_inputs"] = time.perf_counter() - t1
 
         t2 = time.perf_counter()
         if overlap:
             ev[4].record(main)
-        self.t_buf = ops.empty(n, dp)
-        self.w1, self.w2, self.w3 = ops.zeros(Mp, dp), ops.zeros(Mp, dp), ops.zeros(Mp, dp)
-        B = ops.zeros(Mp, dp)
-        Bw = self.w3
-        # rhs = A^-T T^-T K_nM^T (Y / n)
-        ops.axpby(1.0 / self.n_total, Yd, 0.0, Yd)     # Y / n
-        Bw.zero_()
-        ops.kmv(self.spec, self.frame, self.Cprep, self.Xprep, Yd, Bw[:M])
-        self.n_kmv_ += 1
-        self.comm.all_reduce(Bw)
-        del Yd
-        pre.invTt_invAt(Bw, B)            # B = A^-T T^-T K_nM^T (Y / n)
+        # the right-hand sides are solved simultaneously, at most MAX_COLS columns per CG run (the fused
+        # kernel carries up to 32 columns of V); preconditioner and prepared rows are shared by the runs
         pre.check()
-
-        beta = self._conjugate_gradient(B, Mp, dp)
-        alpha = self.w2
-        pre.invA_invT(beta, alpha)        # alpha = T^-1 A^-1 beta
-        beta = alpha
+        out = ops.zeros(M, d)
+        all_res, n_iter = [], 0
+        for c0 in range(0, d, MAX_COLS):
+            c1 = min(d, c0 + MAX_COLS)
+            dp = pad_cols(c1 - c0)
+            Yd = ops.zeros(n, dp)
+            Yd[:, : c1 - c0] = Yfull[:, c0:c1]
+            alpha = self._solve_columns(Yd, Mp, dp)
+            out[:, c0:c1] = alpha[:M, : c1 - c0]
+            all_res.append(list(self.residuals))
+            n_iter = max(n_iter, self.n_iter_)
+        del Yfull
+        self.n_iter_ = n_iter
+        self.residuals = [max(r[i] for r in all_res if i < len(r)) for i in range(max(len(r) for r in all_res))]
         if overlap:
             self._phase_events[5].record(main)
         ops.synchronize()
@@ -263,7 +257,27 @@ class FalkonSolver:
         else:
             self.times["cg"] = time.perf_counter() - t2
         self.times["fit"] = time.perf_counter() - t0
-        return beta[:M, :d].contiguous()
+        return out
+
+    def _solve_columns(self, Yd, Mp, dp):
+        """FALKON solve for the (padded) columns Yd [n x dp]; returns alpha [Mp x dp] (a scratch buffer)."""
+        ops, pre, M = self.ops, self.pre, self.M
+        n = Yd.shape[0]
+        self.t_buf = ops.empty(n, dp)
+        self.w1, self.w2, self.w3 = ops.zeros(Mp, dp), ops.zeros(Mp, dp), ops.zeros(Mp, dp)
+        B = ops.zeros(Mp, dp)
+        Bw = self.w3
+        # rhs = A^-T T^-T K_nM^T (Y / n)
+        ops.axpby(1.0 / self.n_total, Yd, 0.0, Yd)     # Y / n
+        Bw.zero_()
+        ops.kmv(self.spec, self.frame, self.Cprep, self.Xprep, Yd, Bw[:M])
+        self.n_kmv_ += 1
+        self.comm.all_reduce(Bw)
+        pre.invTt_invAt(Bw, B)            # B = A^-T T^-T K_nM^T (Y / n)
+        beta = self._conjugate_gradient(B, Mp, dp)
+        alpha = self.w2
+        pre.invA_invT(beta, alpha)        # alpha = T^-1 A^-1 beta
+        return alpha
 
     def _conjugate_gradient(self, B, Mp, dp):
         ops = self.ops
@@ -312,16 +326,21 @@ class Predictor:
         self.frame = ops.make_frame(C, spec)
         self.Cprep = ops.prepare(C, self.frame)
         self.d = alpha.shape[1]
-        self.dp = pad_cols(self.d)
-        if self.dp > 32:
-            raise NotImplementedError("more than 32 output columns")
-        self.alpha = ops.zeros(C.shape[0], self.dp)
-        self.alpha[:, : self.d] = ops.to_device(alpha)
+        alpha_d = ops.to_device(alpha)
+        self.alpha_chunks = []      # (first column, padded coefficient block) per <= MAX_COLS columns
+        for c0 in range(0, self.d, MAX_COLS):
+            c1 = min(self.d, c0 + MAX_COLS)
+            blk = ops.zeros(C.shape[0], pad_cols(c1 - c0))
+            blk[:, : c1 - c0] = alpha_d[:, c0:c1]
+            self.alpha_chunks.append((c0, c1, blk))
 
     def predict(self, X: torch.Tensor, row_chunk: int = 262144) -> torch.Tensor:
         ops = self.ops
-        out = ops.zeros(X.shape[0], self.dp)
+        out = ops.zeros(X.shape[0], self.d)
         for s in range(0, X.shape[0], row_chunk):
             Xp = ops.prepare(X[s : s + row_chunk], self.frame)
-            ops.kmv(self.spec, self.frame, Xp, self.Cprep, self.alpha, out[s : s + row_chunk])
-        return out[:, : self.d]
+            for c0, c1, blk in self.alpha_chunks:
+                part = ops.zeros(Xp.n, blk.shape[1])
+                ops.kmv(self.spec, self.frame, Xp, self.Cprep, blk, part)
+                out[s : s + row_chunk, c0:c1] = part[:, : c1 - c0]
+        return out

@@ -95,6 +95,21 @@ def test_fit_matches_oracle_ragged_shapes():
     assert relerr(clf.transform(Xv), fo.falkon_predict(Xv, X[idx], ref, "matern", 8.0, 1.5)) < PRED_TOL
 
 
+def test_more_than_32_latent_columns():
+    """d = 40: the right-hand sides are solved in two runs of <= 32 columns, predictions likewise."""
+    Xall = syn.log_counts_numpy(1540, 120, seed=12)
+    Yall = torch.from_numpy(syn.targets_numpy(Xall, 40, seed=13))
+    X, Xv, Y = torch.from_numpy(Xall[:1500]), torch.from_numpy(Xall[1500:]), Yall[:1500]
+    idx = syn.centre_indices(1500, 200, seed=3)
+    clf = _fit_with_centres(KRRApprox(method="falkon", kernel="laplacian", kernel_params={"sigma": 6.0},
+                                      penalization=1e-4, M=200), X, Y, idx)
+    assert clf.sample_weights_.shape == (200, 40)
+    pred = clf.transform(Xv)
+    alpha = fo.falkon_fit(X, Y, X[idx], "laplacian", 6.0, 1e-4)
+    ref = fo.falkon_predict(Xv, X[idx], alpha, "laplacian", 6.0)
+    assert pred.shape == (40, 40) and relerr(pred, ref) < PRED_TOL
+
+
 def test_cuda_inputs_stay_on_device():
     X, Xv, W, Y, Yv = krr_test_data(seed=3, n=900, p=50, d=4)
     est = Falkon(kernel=LaplacianKernel(sigma=10.0), penalty=1e-4, M=200, seed=0)

@@ -114,6 +114,17 @@ def test_solver_matches_oracle_single_process(family, okernel, nu):
     assert solver.n_kmv_ == 1 + 2 * (solver.n_iter_ + full_grads)
 
 
+def test_solver_splits_more_than_32_columns():
+    """d = 40 latent columns: two CG runs (32 + 8) sharing the preconditioner; same answer as the oracle."""
+    X, Xv, W, Y, Yv = krr_test_data(seed=6, n=500, p=20, d=40)
+    C = X[:100]
+    alpha, solver = _fit_cpu(X, Y, C, "gaussian", 6.0, 1e-4)
+    ref = fo.falkon_fit(X, Y, C, "rbf", 6.0, 1e-4)
+    assert alpha.shape == (100, 40)
+    assert relerr(alpha, ref) < 1e-6
+    assert solver.n_kmv_ == 2 * (1 + 2 * (solver.n_iter_ + 1))
+
+
 def test_solver_stops_on_tolerance():
     X, Xv, W, Y, Yv = krr_test_data(seed=5, n=200, p=10, d=2)
     # M = n and a negligible jitter: the preconditioner is exact, CG converges at once
