@@ -583,6 +583,7 @@ struct TrsmJob {
 struct TrsmJobs {
   TrsmJob job[2];
   int njobs;
+  long long* trace;  // developer tool (SAB_TRSM_TRACE_PTR): per block 8 globaltimer stamps of the last chain step
 };
 
 template <int DP, bool TRANS>
@@ -683,10 +684,19 @@ trsm_chain_kernel(const TrsmJobs jobs, int nblk, int* __restrict__ sync) {
     for (int i = 0; i < 4; ++i) bfrag[nb][i] = 0.f;
   if (jid == 0) load_rhs();
 
+  auto stamp = [&](int slot) {
+    if (jobs.trace != nullptr && jid == 0 && threadIdx.x == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      jobs.trace[8 * blk + slot] = static_cast<long long>(now);
+    }
+  };
   bool have_x = false;  // x of the current dependency was prefetched by the previous iteration
   for (int d = 0; d < c; ++d) {
     if (threadIdx.x == 0) {
+      if (d == c - 1) stamp(0);
       if (!have_x) wait_flag(flags + src_of(d), src_of(d));
+      if (d == c - 1) stamp(1);
       s_next = (d + 1 < c) ? ld_acquire_gpu(flags + src_of(d + 1)) : 0;
     }
     __syncthreads();  // x_src is published; everyone is done with slot (d + 1) & 1 of both rings
@@ -700,8 +710,10 @@ trsm_chain_kernel(const TrsmJobs jobs, int nblk, int* __restrict__ sync) {
     cp_async_commit();
     cp_async_wait<1>();  // everything but that newest group: tile d and x_d have landed
     __syncthreads();
+    if (d == c - 1) stamp(2);
     float acc[NB8][4];
     tile_times_rhs<NB8, TRANS>(ring + (d & 1) * TS * LT, xring + (d & 1) * TS * LX, acc);
+    if (d == c - 1) stamp(3);
 #pragma unroll
     for (int nb = 0; nb < NB8; ++nb)
 #pragma unroll
@@ -725,8 +737,10 @@ trsm_chain_kernel(const TrsmJobs jobs, int nblk, int* __restrict__ sync) {
     xs[(m0 + g + 8) * LX + cc + 1] = bfrag[nb][3];
   }
   __syncthreads();
+  stamp(4);
   float acc[NB8][4];
   tile_times_rhs<NB8, TRANS>(ring + (c & 1) * TS * LT, xs, acc);
+  stamp(5);
 #pragma unroll
   for (int nb = 0; nb < NB8; ++nb) {
     const int cc = nb * 8 + 2 * t;
@@ -737,8 +751,10 @@ trsm_chain_kernel(const TrsmJobs jobs, int nblk, int* __restrict__ sync) {
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    stamp(6);
     __threadfence();
     st_release_gpu(flags + blk, 1);
+    stamp(7);
   }
 }
 
@@ -991,6 +1007,10 @@ static int trsm_launch(cudaStream_t st, const float* L, long long M, long long l
     TrsmJobs jobs = {};
     jobs.njobs = 1;
     jobs.job[0] = TrsmJob{L, ldl, invdiag, B, B, nullptr, 0.f};
+    {
+      const char* tp = std::getenv("SAB_TRSM_TRACE_PTR");
+      jobs.trace = tp ? reinterpret_cast<long long*>(std::strtoull(tp, nullptr, 0)) : nullptr;
+    }
     return trsm_chain_launch<DP>(st, jobs, M, transpose, sync);
   }
   const int smem = (TS * trsm_ldt(transpose != 0) + TS * trsm_ldx((DP + 7) / 8)) * static_cast<int>(sizeof(float));
