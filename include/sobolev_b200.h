@@ -58,6 +58,24 @@ int sa_prep(void* stream, const float* X, int64_t n, int64_t p, int64_t ldx, con
             int64_t norms_len);
 
 /*
+ * Input preprocessing of the artificial samples before the fit (SobolevAlignment._memmap_log_processing
+ * and _frobenius_normalisation, sobolev_alignment.py:830-902: np.log10(x + 1), StandardScaler, one
+ * scalar per data source), as two streaming passes on the device.
+ * sa_colstats: sum[j] += sum_i y_ij, sumsq[j] += sum_i y_ij^2 with y_ij = f(X[i, j]) - pivot[j], f = log10(x + 1)
+ * when log10p1 != 0, else the identity; pivot (may be NULL = 0) should lie near the column mean (e.g. f of the
+ * first row) so that the variance sumsq/n - (sum/n)^2 does not cancel; float64 accumulators, ACCUMULATED INTO
+ * (the caller zeroes them; at most 65535 * 4096 rows per call).
+ * sa_transform_rows: out[i, j] = (f(X[i, j]) - shift[j]) * scale[j] * gain (shift / scale may be NULL; out may
+ * alias X); rownorm_sum (may be NULL) += sum_i |out[i, :]|_2, the numerator of the mean row norm of the
+ * Frobenius normalisation.
+ */
+int sa_colstats(void* stream, const float* X, int64_t n, int64_t p, int64_t ldx, int log10p1,
+                const float* pivot, double* sum, double* sumsq);
+int sa_transform_rows(void* stream, const float* X, int64_t n, int64_t p, int64_t ldx, int log10p1,
+                      const float* shift, const float* scale, float gain, float* out, int64_t ldo,
+                      double* rownorm_sum);
+
+/*
  * Fused kernel-matrix x matrix product, K never materialised (falkon `Kernel.mmv` and each half of
  * `Kernel.dmmv` [ext]; reached from `Falkon.fit` krr_approx.py:227 and `Falkon.predict` :314):
  *   out[a x dp] += k(A, B) @ V[b x dp]

@@ -66,6 +66,9 @@ _SIGNATURES = {
     "sa_device_info": (c_int, [c_void_p, c_void_p]),
     "sa_prep": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_float,
                         c_void_p, c_int64, c_void_p, c_int64]),
+    "sa_colstats": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "sa_transform_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_float,
+                                  c_void_p, c_int64, c_void_p]),
     "sa_kmv_workspace_bytes": (c_int64, [c_int64, c_int]),
     "sa_kmv": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
                        c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64]),
@@ -174,6 +177,44 @@ def prep(X: torch.Tensor, shift: torch.Tensor | None, scale: torch.Tensor | None
                        float(gscale), dptr, out.p_pad, nptr, norms_len))
     STATS.launches += 1
     return out
+
+
+def colstats(X: torch.Tensor, log10p1: bool):
+    """Per-column (mean, population variance) of f(X), f = log10(x + 1) or identity; float64 CUDA tensors [p]."""
+    lib = load()
+    if not X.is_cuda or X.dtype != torch.float32 or X.dim() != 2 or X.stride(1) != 1:
+        raise NativeLibraryError("colstats expects a 2-D float32 CUDA tensor with unit column stride")
+    n, p = X.shape
+    s1 = torch.zeros(p, dtype=torch.float64, device=X.device)
+    s2 = torch.zeros(p, dtype=torch.float64, device=X.device)
+    # pivot = f(first row): sums of (y - pivot) keep the variance free of cancellation
+    pivot = torch.empty(1, p, dtype=torch.float32, device=X.device)
+    _check(lib.sa_transform_rows(_stream(), X.data_ptr(), 1, p, X.stride(0), int(log10p1), None, None, 1.0,
+                                 pivot.data_ptr(), p, None))
+    step = 65535 * 4096
+    for r0 in range(0, n, step):
+        r1 = min(n, r0 + step)
+        _check(lib.sa_colstats(_stream(), X[r0:r1].data_ptr(), r1 - r0, p, X.stride(0), int(log10p1),
+                               pivot.data_ptr(), s1.data_ptr(), s2.data_ptr()))
+        STATS.launches += 2
+    m = s1 / n
+    var = (s2 / n - m * m).clamp_min_(0.0)
+    return pivot.view(-1).double() + m, var
+
+
+def transform_rows(X: torch.Tensor, log10p1: bool, shift: torch.Tensor | None, scale: torch.Tensor | None,
+                   gain: float = 1.0, want_row_norms: bool = False):
+    """In place X <- (f(X) - shift) * scale * gain; returns sum_i |X_i|_2 (float64 scalar tensor) if asked."""
+    lib = load()
+    if not X.is_cuda or X.dtype != torch.float32 or X.dim() != 2 or X.stride(1) != 1:
+        raise NativeLibraryError("transform_rows expects a 2-D float32 CUDA tensor with unit column stride")
+    n, p = X.shape
+    acc = torch.zeros(1, dtype=torch.float64, device=X.device) if want_row_norms else None
+    if n:
+        _check(lib.sa_transform_rows(_stream(), X.data_ptr(), n, p, X.stride(0), int(log10p1), _ptr(shift), _ptr(scale),
+                                     float(gain), X.data_ptr(), X.stride(0), _ptr(acc)))
+        STATS.launches += 1
+    return acc
 
 
 def alloc_prepared(n: int, p: int, device) -> Prepared:

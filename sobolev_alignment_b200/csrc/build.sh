@@ -8,12 +8,12 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
        --expt-relaxed-constexpr -Xptxas -v ${SAB_NVCC_EXTRA:-})
 pids=()
-for f in api kmv prep linalg; do
+for f in api kmv prep preproc linalg; do
   ( "${NVCC}" "${FLAGS[@]}" -c "${HERE}/${f}.cu" -o "${HERE}/.obj/${f}.o" > "${HERE}/.obj/${f}.log" 2>&1 ) &
   pids+=($!)
 done
 rc=0
 for p in "${pids[@]}"; do wait "$p" || rc=1; done
 if [ "$rc" -ne 0 ]; then cat "${HERE}"/.obj/*.log; exit 1; fi
-"${NVCC}" -shared -o "${OUT}/libsobolev_b200.so" "${HERE}"/.obj/{api,kmv,prep,linalg}.o -cudart static
+"${NVCC}" -shared -o "${OUT}/libsobolev_b200.so" "${HERE}"/.obj/{api,kmv,prep,preproc,linalg}.o -cudart static
 echo "built ${OUT}/libsobolev_b200.so"

@@ -1,0 +1,119 @@
+// Input preprocessing of the artificial samples on the device: the chain
+// /root/reference/sobolev_alignment/sobolev_alignment.py:830-902 (`_memmap_log_processing`,
+// `_frobenius_normalisation`) runs on the host in numpy today -- log10(x + 1), StandardScaler, one scalar
+// per data source -- i.e. three full passes over a 12 GB array before `KRRApprox.fit` sees it.  Here:
+//   sa_colstats        per-column sum / sum of squares of f(x) - pivot (f = identity or log10(x + 1)), float64
+//   sa_transform_rows  out = (f(x) - shift) * scale * gain   (fp32, may be in place) + sum of row norms
+// Both are HBM-bound streaming kernels (n*p*4 bytes read, + n*p*4 written for the transform).
+#include "../../include/sobolev_b200.h"
+#include "common.cuh"
+
+namespace sab {
+namespace pre {
+
+__device__ __forceinline__ float fwd(float x, int log10p1) { return log10p1 ? log10f(x + 1.0f) : x; }
+
+constexpr int CS_ROWS = 8;  // blockDim = (32, CS_ROWS): 32 consecutive columns x 8 interleaved rows
+
+__global__ void __launch_bounds__(32 * CS_ROWS)
+colstats_kernel(const float* __restrict__ X, long long n, int p, long long ldx, int log10p1, long long rows_per_block,
+                const float* __restrict__ pivot, double* __restrict__ sum, double* __restrict__ sumsq) {
+  __shared__ double s1[CS_ROWS][32], s2[CS_ROWS][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  const long long r1 = min(n, r0 + rows_per_block);
+  double a = 0.0, b = 0.0;
+  if (c < p) {
+    // Sums of (y - pivot): with the pivot near the column mean, var = E[(y-c)^2] - E[y-c]^2 does not cancel.
+    // float partial sums over 64 rows, folded into float64.
+    const float pv = pivot ? __ldg(pivot + c) : 0.f;
+    for (long long r = r0 + threadIdx.y; r < r1; r += CS_ROWS * 64) {
+      float fa = 0.f, fb = 0.f;
+      for (long long rr = r; rr < min(r1, r + CS_ROWS * 64); rr += CS_ROWS) {
+        const float y = fwd(__ldcs(X + rr * ldx + c), log10p1) - pv;
+        fa += y;
+        fb = fmaf(y, y, fb);
+      }
+      a += fa;
+      b += fb;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < p) {
+#pragma unroll
+    for (int k = 1; k < CS_ROWS; ++k) {
+      a += s1[k][threadIdx.x];
+      b += s2[k][threadIdx.x];
+    }
+    atomicAdd(sum + c, a);
+    atomicAdd(sumsq + c, b);
+  }
+}
+
+constexpr int TR_WARPS = 8;
+
+__global__ void __launch_bounds__(TR_WARPS * 32)
+transform_rows_kernel(const float* __restrict__ X, long long n, int p, long long ldx, int log10p1,
+                      const float* __restrict__ shift, const float* __restrict__ scale, float gain,
+                      float* __restrict__ out, long long ldo, double* __restrict__ rownorm_sum) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = static_cast<long long>(blockIdx.x) * TR_WARPS + (threadIdx.x >> 5);
+  const long long warp_stride = static_cast<long long>(gridDim.x) * TR_WARPS;
+  double local = 0.0;
+  for (long long row = warp_global; row < n; row += warp_stride) {
+    const float* x = X + row * ldx;
+    float* o = out + row * ldo;
+    float acc = 0.f;
+    for (int j = lane; j < p; j += 32) {
+      const float sh = shift ? __ldg(shift + j) : 0.f;
+      const float sc = scale ? __ldg(scale + j) : 1.f;
+      const float y = (fwd(x[j], log10p1) - sh) * sc * gain;
+      acc = fmaf(y, y, acc);
+      o[j] = y;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    local += static_cast<double>(sqrtf(acc));
+  }
+  if (rownorm_sum != nullptr && lane == 0) atomicAdd(rownorm_sum, local);
+}
+
+}  // namespace pre
+}  // namespace sab
+
+extern "C" int sa_colstats(void* stream, const float* X, int64_t n, int64_t p, int64_t ldx, int log10p1,
+                           const float* pivot, double* sum, double* sumsq) {
+  using namespace sab;
+  SAB_REQUIRE(n >= 0 && p > 0 && p < (1ll << 30) && ldx >= p, "bad shape n=%lld p=%lld ldx=%lld", (long long)n,
+              (long long)p, (long long)ldx);
+  SAB_REQUIRE(sum != nullptr && sumsq != nullptr, "NULL output");
+  if (n == 0) return 0;
+  const long long rows_per_block = 4096;
+  dim3 grid(static_cast<unsigned>(ceil_div(p, 32)), static_cast<unsigned>(ceil_div(n, rows_per_block)));
+  SAB_REQUIRE(grid.y <= 65535, "too many rows for one call (%lld): call per row chunk", (long long)n);
+  pre::colstats_kernel<<<grid, dim3(32, pre::CS_ROWS), 0, static_cast<cudaStream_t>(stream)>>>(
+      X, n, static_cast<int>(p), ldx, log10p1, rows_per_block, pivot, sum, sumsq);
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sa_transform_rows(void* stream, const float* X, int64_t n, int64_t p, int64_t ldx, int log10p1,
+                                 const float* shift, const float* scale, float gain, float* out, int64_t ldo,
+                                 double* rownorm_sum) {
+  using namespace sab;
+  SAB_REQUIRE(n >= 0 && p > 0 && p < (1ll << 30) && ldx >= p && ldo >= p, "bad shape n=%lld p=%lld", (long long)n,
+              (long long)p);
+  SAB_REQUIRE(out != nullptr, "NULL output");
+  if (n == 0) return 0;
+  int dev = 0, sms = 0;
+  SAB_CHECK_CUDA(cudaGetDevice(&dev));
+  SAB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long blocks = ceil_div(n, pre::TR_WARPS);
+  if (blocks > static_cast<long long>(sms) * 8) blocks = static_cast<long long>(sms) * 8;
+  pre::transform_rows_kernel<<<static_cast<int>(blocks), pre::TR_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      X, n, static_cast<int>(p), ldx, log10p1, shift, scale, gain, out, ldo, rownorm_sum);
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

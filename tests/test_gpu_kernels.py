@@ -119,6 +119,35 @@ def test_prepare_back_to_back_host_inputs(cuda_ops):
         assert torch.equal(Ps.data, ref_s.data) and torch.equal(Ps.norms, ref_s.norms)
 
 
+# ---------------------------------------------------------------------------- input preprocessing
+@pytest.mark.parametrize("log_input,mean_center,unit_std,frob", [(True, True, True, True), (True, False, True, False),
+                                                                 (True, True, False, True), (False, False, False, True),
+                                                                 (True, False, False, False)])
+def test_input_preprocessor_matches_oracle(log_input, mean_center, unit_std, frob, tmp_path):
+    """Device version of SobolevAlignment._memmap_log_processing against the float64 restatement; memmap input."""
+    from oracle.preprocess_oracle import PreprocessOracle
+    from sobolev_alignment_b200.preprocessing import InputPreprocessor
+
+    rng = np.random.default_rng(17)
+    rates = rng.integers(1, 25, size=333)
+    src = rng.poisson(rates[None, :] * rng.lognormal(0, 0.25, size=(5003, 1))).astype(np.float32)
+    tgt = rng.poisson(rates[None, :] * rng.lognormal(0, 0.3, size=(2001, 1))).astype(np.float32)
+    src[:, 11] = 2.0                                     # constant gene
+    path = tmp_path / "src.npy"
+    np.save(path, src)
+    src_mm = np.load(path, mmap_mode="r")               # the reference hands over read-only memmaps
+    dev = InputPreprocessor(log_input, mean_center, unit_std, frob, chunk_rows=1024)
+    orc = PreprocessOracle(log_input, mean_center, unit_std, frob)
+    for name, data in (("source", src_mm), ("target", tgt)):
+        got = dev.fit_transform(name, data)
+        ref = orc.fit_transform(name, np.asarray(data))
+        assert got.is_cuda and got.dtype == torch.float32 and got.shape == ref.shape
+        assert relerr(got, torch.from_numpy(ref)) < 1e-5      # fp32 log10 / affine map against float64
+    if frob:
+        assert abs(dev.frob_norm_param_ / orc.frob_norm_param - 1) < 1e-6
+    assert np.array_equal(np.load(path), src)           # the input was not written
+
+
 # ---------------------------------------------------------------------------- fused kmv
 @pytest.mark.parametrize("family,okernel,nu", FAMILIES)
 @pytest.mark.parametrize("a,b,p,d", [(1, 1, 1, 1), (128, 256, 64, 4), (300, 500, 100, 7), (2000, 500, 500, 10),

@@ -95,3 +95,33 @@ def test_mat_inv_sqrt_identity():
     M = B @ B.T + 0.1 * np.eye(6)
     S = fo.mat_inv_sqrt(M)
     assert np.allclose(S @ M @ S, np.eye(6), atol=1e-10)
+
+
+# ---------------------------------------------------------------------------- preprocessing chain
+def test_preprocess_oracle_matches_sklearn_and_the_reference_lines():
+    """
+    The restatement of sobolev_alignment.py:851-902 against the calls the reference itself makes:
+    np.log10(x + 1), sklearn StandardScaler(with_mean, with_std).fit_transform, mean row norm scaling.
+    """
+    from sklearn.preprocessing import StandardScaler
+
+    from oracle.preprocess_oracle import PreprocessOracle
+
+    rng = np.random.default_rng(3)
+    src = rng.poisson(rng.integers(1, 25, size=40)[None, :] * rng.lognormal(0, 0.25, size=(300, 1))).astype(np.float64)
+    tgt = rng.poisson(rng.integers(1, 25, size=40)[None, :] * rng.lognormal(0, 0.25, size=(200, 1))).astype(np.float64)
+    src[:, 7] = 3.0                          # constant genes: StandardScaler leaves their scale at 1
+    src[:, 9] = 2.0                          # (log10(3) does not average exactly: sklearn's round-off rule)
+    tgt[:, 5] = 0.0
+    for mc in (False, True):
+        for us in (False, True):
+            orc = PreprocessOracle(log_input=True, mean_center=mc, unit_std=us, frob_norm_source=True)
+            got_s, got_t = orc.fit_transform("source", src), orc.fit_transform("target", tgt)
+            ref_s = StandardScaler(with_mean=mc, with_std=us).fit_transform(np.log10(src + 1))
+            ref_t = StandardScaler(with_mean=mc, with_std=us).fit_transform(np.log10(tgt + 1))
+            param = np.mean(np.linalg.norm(ref_s, axis=1))
+            ref_t = ref_t * param / np.mean(np.linalg.norm(ref_t, axis=1))
+            assert np.allclose(got_s, ref_s, rtol=0, atol=1e-12) and np.allclose(got_t, ref_t, rtol=0, atol=1e-12)
+            assert abs(orc.frob_norm_param - param) < 1e-12
+    raw = PreprocessOracle(log_input=False, frob_norm_source=False).fit_transform("source", src)
+    assert np.array_equal(raw, src)
