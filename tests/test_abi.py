@@ -57,6 +57,10 @@ def test_product_path_fails_loudly_without_cuda():
         clf.fit(torch.zeros(16, 4), torch.zeros(16, 2))
     with pytest.raises(NativeLibraryError):
         clf.kernel_(torch.zeros(4, 4), torch.zeros(4, 4))
+    from sobolev_alignment_b200.preprocessing import InputPreprocessor
+
+    with pytest.raises(NativeLibraryError):
+        InputPreprocessor(log_input=True)
 
 
 def test_product_package_never_imports_the_oracle():
