@@ -13,47 +13,93 @@ namespace pre {
 
 __device__ __forceinline__ float fwd(float x, int log10p1) { return log10p1 ? log10f(x + 1.0f) : x; }
 
-constexpr int CS_ROWS = 8;  // blockDim = (32, CS_ROWS): 32 consecutive columns x 8 interleaved rows
+constexpr int CS_ROWS = 8;  // blockDim = (32, CS_ROWS): 32 x 4 consecutive columns, 8 interleaved rows
 
+// VEC: every thread owns 4 consecutive columns (128-bit loads, 512 B per warp and row); rows are walked 4 at
+// a time so that 4 independent loads are in flight per thread
+template <bool VEC>
 __global__ void __launch_bounds__(32 * CS_ROWS)
 colstats_kernel(const float* __restrict__ X, long long n, int p, long long ldx, int log10p1, long long rows_per_block,
                 const float* __restrict__ pivot, double* __restrict__ sum, double* __restrict__ sumsq) {
-  __shared__ double s1[CS_ROWS][32], s2[CS_ROWS][32];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  constexpr int W = VEC ? 4 : 1;
+  __shared__ double s1[CS_ROWS][32 * W], s2[CS_ROWS][32 * W];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * W;
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
   const long long r1 = min(n, r0 + rows_per_block);
-  double a = 0.0, b = 0.0;
+  double a[W], b[W];
+  float pv[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    a[w] = b[w] = 0.0;
+    pv[w] = (pivot && c + w < p) ? __ldg(pivot + c + w) : 0.f;
+  }
   if (c < p) {
     // Sums of (y - pivot): with the pivot near the column mean, var = E[(y-c)^2] - E[y-c]^2 does not cancel.
     // float partial sums over 64 rows, folded into float64.
-    const float pv = pivot ? __ldg(pivot + c) : 0.f;
     for (long long r = r0 + threadIdx.y; r < r1; r += CS_ROWS * 64) {
-      float fa = 0.f, fb = 0.f;
-      for (long long rr = r; rr < min(r1, r + CS_ROWS * 64); rr += CS_ROWS) {
-        const float y = fwd(__ldcs(X + rr * ldx + c), log10p1) - pv;
-        fa += y;
-        fb = fmaf(y, y, fb);
+      float fa[W], fb[W];
+#pragma unroll
+      for (int w = 0; w < W; ++w) fa[w] = fb[w] = 0.f;
+      const long long rend = min(r1, r + CS_ROWS * 64);
+      long long rr = r;
+      if (VEC) {
+        for (; rr + 3 * CS_ROWS < rend; rr += 4 * CS_ROWS) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(X + (rr + u * CS_ROWS) * ldx + c));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float y[4] = {fwd(v[u].x, log10p1) - pv[0], fwd(v[u].y, log10p1) - pv[1],
+                                fwd(v[u].z, log10p1) - pv[2], fwd(v[u].w, log10p1) - pv[3]};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              fa[w] += y[w];
+              fb[w] = fmaf(y[w], y[w], fb[w]);
+            }
+          }
+        }
       }
-      a += fa;
-      b += fb;
+      for (; rr < rend; rr += CS_ROWS) {
+#pragma unroll
+        for (int w = 0; w < W; ++w)
+          if (c + w < p) {
+            const float y = fwd(__ldcs(X + rr * ldx + c + w), log10p1) - pv[w];
+            fa[w] += y;
+            fb[w] = fmaf(y, y, fb[w]);
+          }
+      }
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        a[w] += fa[w];
+        b[w] += fb[w];
+      }
     }
   }
-  s1[threadIdx.y][threadIdx.x] = a;
-  s2[threadIdx.y][threadIdx.x] = b;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < p) {
 #pragma unroll
-    for (int k = 1; k < CS_ROWS; ++k) {
-      a += s1[k][threadIdx.x];
-      b += s2[k][threadIdx.x];
+  for (int w = 0; w < W; ++w) {
+    s1[threadIdx.y][threadIdx.x * W + w] = a[w];
+    s2[threadIdx.y][threadIdx.x * W + w] = b[w];
+  }
+  __syncthreads();
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      if (c + w >= p) continue;
+      double ta = a[w], tb = b[w];
+#pragma unroll
+      for (int k = 1; k < CS_ROWS; ++k) {
+        ta += s1[k][threadIdx.x * W + w];
+        tb += s2[k][threadIdx.x * W + w];
+      }
+      atomicAdd(sum + c + w, ta);
+      atomicAdd(sumsq + c + w, tb);
     }
-    atomicAdd(sum + c, a);
-    atomicAdd(sumsq + c, b);
   }
 }
 
 constexpr int TR_WARPS = 8;
 
+template <bool VEC>
 __global__ void __launch_bounds__(TR_WARPS * 32)
 transform_rows_kernel(const float* __restrict__ X, long long n, int p, long long ldx, int log10p1,
                       const float* __restrict__ shift, const float* __restrict__ scale, float gain,
@@ -66,7 +112,25 @@ transform_rows_kernel(const float* __restrict__ X, long long n, int p, long long
     const float* x = X + row * ldx;
     float* o = out + row * ldo;
     float acc = 0.f;
-    for (int j = lane; j < p; j += 32) {
+    int j0 = 0;
+    if (VEC) {
+      const int p4 = p >> 2;
+      for (int q = lane; q < p4; q += 32) {
+        const float4 v = reinterpret_cast<const float4*>(x)[q];
+        float4 sh = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift) + q);
+        if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale) + q);
+        float4 y;
+        y.x = (fwd(v.x, log10p1) - sh.x) * sc.x * gain;
+        y.y = (fwd(v.y, log10p1) - sh.y) * sc.y * gain;
+        y.z = (fwd(v.z, log10p1) - sh.z) * sc.z * gain;
+        y.w = (fwd(v.w, log10p1) - sh.w) * sc.w * gain;
+        acc = fmaf(y.x, y.x, fmaf(y.y, y.y, fmaf(y.z, y.z, fmaf(y.w, y.w, acc))));
+        reinterpret_cast<float4*>(o)[q] = y;
+      }
+      j0 = p4 << 2;
+    }
+    for (int j = j0 + lane; j < p; j += 32) {
       const float sh = shift ? __ldg(shift + j) : 0.f;
       const float sc = scale ? __ldg(scale + j) : 1.f;
       const float y = (fwd(x[j], log10p1) - sh) * sc * gain;
@@ -91,10 +155,15 @@ extern "C" int sa_colstats(void* stream, const float* X, int64_t n, int64_t p, i
   SAB_REQUIRE(sum != nullptr && sumsq != nullptr, "NULL output");
   if (n == 0) return 0;
   const long long rows_per_block = 4096;
-  dim3 grid(static_cast<unsigned>(ceil_div(p, 32)), static_cast<unsigned>(ceil_div(n, rows_per_block)));
+  const bool vec = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  dim3 grid(static_cast<unsigned>(ceil_div(p, vec ? 128 : 32)), static_cast<unsigned>(ceil_div(n, rows_per_block)));
   SAB_REQUIRE(grid.y <= 65535, "too many rows for one call (%lld): call per row chunk", (long long)n);
-  pre::colstats_kernel<<<grid, dim3(32, pre::CS_ROWS), 0, static_cast<cudaStream_t>(stream)>>>(
-      X, n, static_cast<int>(p), ldx, log10p1, rows_per_block, pivot, sum, sumsq);
+  if (vec)
+    pre::colstats_kernel<true><<<grid, dim3(32, pre::CS_ROWS), 0, static_cast<cudaStream_t>(stream)>>>(
+        X, n, static_cast<int>(p), ldx, log10p1, rows_per_block, pivot, sum, sumsq);
+  else
+    pre::colstats_kernel<false><<<grid, dim3(32, pre::CS_ROWS), 0, static_cast<cudaStream_t>(stream)>>>(
+        X, n, static_cast<int>(p), ldx, log10p1, rows_per_block, pivot, sum, sumsq);
   SAB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -112,8 +181,16 @@ extern "C" int sa_transform_rows(void* stream, const float* X, int64_t n, int64_
   SAB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   long long blocks = ceil_div(n, pre::TR_WARPS);
   if (blocks > static_cast<long long>(sms) * 8) blocks = static_cast<long long>(sms) * 8;
-  pre::transform_rows_kernel<<<static_cast<int>(blocks), pre::TR_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      X, n, static_cast<int>(p), ldx, log10p1, shift, scale, gain, out, ldo, rownorm_sum);
+  const bool vec = (ldx % 4 == 0) && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                   (!shift || (reinterpret_cast<uintptr_t>(shift) & 15) == 0) &&
+                   (!scale || (reinterpret_cast<uintptr_t>(scale) & 15) == 0);
+  if (vec)
+    pre::transform_rows_kernel<true><<<static_cast<int>(blocks), pre::TR_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        X, n, static_cast<int>(p), ldx, log10p1, shift, scale, gain, out, ldo, rownorm_sum);
+  else
+    pre::transform_rows_kernel<false><<<static_cast<int>(blocks), pre::TR_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        X, n, static_cast<int>(p), ldx, log10p1, shift, scale, gain, out, ldo, rownorm_sum);
   SAB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

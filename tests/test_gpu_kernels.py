@@ -120,16 +120,17 @@ def test_prepare_back_to_back_host_inputs(cuda_ops):
 
 
 # ---------------------------------------------------------------------------- input preprocessing
+@pytest.mark.parametrize("p", [333, 256])      # scalar and 128-bit vectorised kernels
 @pytest.mark.parametrize("log_input,mean_center,unit_std,frob", [(True, True, True, True), (True, False, True, False),
                                                                  (True, True, False, True), (False, False, False, True),
                                                                  (True, False, False, False)])
-def test_input_preprocessor_matches_oracle(log_input, mean_center, unit_std, frob, tmp_path):
+def test_input_preprocessor_matches_oracle(log_input, mean_center, unit_std, frob, p, tmp_path):
     """Device version of SobolevAlignment._memmap_log_processing against the float64 restatement; memmap input."""
     from oracle.preprocess_oracle import PreprocessOracle
     from sobolev_alignment_b200.preprocessing import InputPreprocessor
 
     rng = np.random.default_rng(17)
-    rates = rng.integers(1, 25, size=333)
+    rates = rng.integers(1, 25, size=p)
     src = rng.poisson(rates[None, :] * rng.lognormal(0, 0.25, size=(5003, 1))).astype(np.float32)
     tgt = rng.poisson(rates[None, :] * rng.lognormal(0, 0.3, size=(2001, 1))).astype(np.float32)
     src[:, 11] = 2.0                                     # constant gene
