@@ -121,6 +121,11 @@ int sa_potrf(void* stream, float* A, int64_t M, int64_t lda, float* invdiag, int
  * same workspace contract as sa_potrf. */
 int sa_ltl(void* stream, const float* L, int64_t M, int64_t ldl, float* G, int64_t ldg, float alpha,
            float beta, void* workspace, int64_t workspace_bytes);
+/* Multi-GPU form: rank `part` of `nparts` accumulates its share of the 512-row slabs of L into G (zeroed by the
+ * caller, no beta term); the caller sums the parts (all-reduce) and adds beta with sa_add_diag.  The slabs are
+ * dealt out from the largest down, so the parts are balanced. */
+int sa_ltl_part(void* stream, const float* L, int64_t M, int64_t ldl, float* G, int64_t ldg, float alpha,
+                float beta, void* workspace, int64_t workspace_bytes, int part, int nparts);
 
 /* A[i, i] += value */
 int sa_add_diag(void* stream, float* A, int64_t M, int64_t lda, float value);

@@ -78,6 +78,8 @@ _SIGNATURES = {
     "sa_potrf": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64]),
     "sa_ltl": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p,
                        c_int64]),
+    "sa_ltl_part": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p,
+                            c_int64, c_int, c_int]),
     "sa_add_diag": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float]),
     "sa_trsm_workspace_bytes": (c_int64, [c_int64]),
     "sa_trsm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64]),
@@ -300,12 +302,13 @@ def potrf(A: torch.Tensor, invdiag: torch.Tensor, info: torch.Tensor):
     STATS.launches += 2 + nblk + 3 * (nblk - 1)   # scale, diagonal blocks, (panel, split, update) per step
 
 
-def ltl(L: torch.Tensor, G: torch.Tensor, alpha: float, beta: float):
+def ltl(L: torch.Tensor, G: torch.Tensor, alpha: float, beta: float, part: int = 0, nparts: int = 1):
+    """G = alpha L^T L + beta I; nparts > 1: this rank's share of the slabs accumulated into a zeroed G (no beta)."""
     _req(L, torch.float32, "L")
     _req(G, torch.float32, "G")
     ws = _linalg_workspace(L.device, L.shape[0])
-    _check(load().sa_ltl(_stream(), L.data_ptr(), L.shape[0], L.stride(0), G.data_ptr(), G.stride(0),
-                         float(alpha), float(beta), ws.data_ptr(), ws.numel()))
+    _check(load().sa_ltl_part(_stream(), L.data_ptr(), L.shape[0], L.stride(0), G.data_ptr(), G.stride(0),
+                              float(alpha), float(beta), ws.data_ptr(), ws.numel(), int(part), int(nparts)))
     STATS.launches += 3 + 2 * (L.shape[0] // TILE)   # scale, (split, update) per block row, diagonal
 
 

@@ -1156,8 +1156,10 @@ extern "C" int sa_potrf(void* stream, float* A, int64_t M, int64_t lda, float* i
   return 0;
 }
 
-extern "C" int sa_ltl(void* stream, const float* L, int64_t M, int64_t ldl, float* G, int64_t ldg,
-                      float alpha, float beta, void* workspace, int64_t workspace_bytes) {
+extern "C" int sa_ltl_part(void* stream, const float* L, int64_t M, int64_t ldl, float* G, int64_t ldg,
+                           float alpha, float beta, void* workspace, int64_t workspace_bytes, int part,
+                           int nparts) {
+  SAB_REQUIRE(nparts >= 1 && part >= 0 && part < nparts, "bad part %d of %d", part, nparts);
   SAB_REQUIRE_MAT(M, ldl, L);
   SAB_REQUIRE_MAT(M, ldg, G);
   SAB_REQUIRE(L != G, "sa_ltl is out of place");
@@ -1166,6 +1168,7 @@ extern "C" int sa_ltl(void* stream, const float* L, int64_t M, int64_t ldl, floa
   const int nblk = static_cast<int>(M / TS);
   SAB_REQUIRE(nblk <= 2048, "matrix order %lld too large", (long long)M);
   if (!use_tensor_path()) {
+    SAB_REQUIRE(nparts == 1, "the fp32 SIMT path computes L^T L in one piece");
     sgemm_kernel<MODE_LTL><<<nblk * (nblk + 1) / 2, 256, 0, st>>>(G, ldg, L, ldl, 0, nblk, alpha, beta);
     SAB_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -1177,13 +1180,16 @@ extern "C" int sa_ltl(void* stream, const float* L, int64_t M, int64_t ldl, floa
   make_scale_kernel<<<1, 1, 0, st>>>(w.hdr, 0);
   // G = alpha sum_b L_b^T L_b over slabs of block rows; slab b = rows [r0, r1) touches G[0 .. r1)^2.
   // Starting with the last slab, the first update of every tile is the one with gamma = 0.
+  // nparts > 1: only the slabs b = part (mod nparts) are accumulated INTO G (which the caller has zeroed) and
+  // no diagonal term is added: the parts of the ranks are summed by an all-reduce, then beta goes on top.
   const int nslab = static_cast<int>(ceil_div(nblk, nbb));
   for (int b = nslab - 1; b >= 0; --b) {
+    if (nparts > 1 && (nslab - 1 - b) % nparts != part) continue;  // counted from the last (largest) slab
     const int b0 = b * nbb, b1 = (b + 1) * nbb < nblk ? (b + 1) * nbb : nblk;
     const long long rows = static_cast<long long>(b1) * TS;  // non-zero columns of the slab
     const int W = (b1 - b0) * TS;
     const float* slab = L + static_cast<long long>(b0) * TS * ldl;
-    const float gamma = (b == nslab - 1) ? 0.f : 1.f;
+    const float gamma = (nparts == 1 && b == nslab - 1) ? 0.f : 1.f;
     exact_diag_t_kernel<<<static_cast<int>(ceil_div(rows, 256)), 256, 0, st>>>(
         G, ldg, slab, ldl, rows, W, static_cast<long long>(b0) * TS, gamma, alpha, w.dsave);
     split_f16_kernel<<<static_cast<int>(ceil_div(rows * (W / 8), 256)), 256, 0, st>>>(
@@ -1194,9 +1200,14 @@ extern "C" int sa_ltl(void* stream, const float* L, int64_t M, int64_t ldl, floa
       return rc;
     restore_diag_kernel<<<static_cast<int>(ceil_div(rows, 256)), 256, 0, st>>>(G, ldg, rows, w.dsave);
   }
-  add_diag_kernel<<<static_cast<int>(ceil_div(M, 256)), 256, 0, st>>>(G, M, ldg, beta);
+  if (nparts == 1) add_diag_kernel<<<static_cast<int>(ceil_div(M, 256)), 256, 0, st>>>(G, M, ldg, beta);
   SAB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int sa_ltl(void* stream, const float* L, int64_t M, int64_t ldl, float* G, int64_t ldg,
+                      float alpha, float beta, void* workspace, int64_t workspace_bytes) {
+  return sa_ltl_part(stream, L, M, ldl, G, ldg, alpha, beta, workspace, workspace_bytes, 0, 1);
 }
 
 extern "C" int sa_add_diag(void* stream, float* A, int64_t M, int64_t lda, float value) {

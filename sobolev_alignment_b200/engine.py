@@ -56,6 +56,7 @@ class Frame:
 
 class CudaOps:
     name = "cuda"
+    ltl_sharded = True     # L^T L can be formed in parts (sa_ltl_part) and summed over the ranks
 
     def __init__(self, device=None, stage_rows: int = 65536):
         if not torch.cuda.is_available():

@@ -60,7 +60,7 @@ class Comm:
 class Preconditioner:
     """Lower Cholesky factors L (= T^T) and LA (= A^T) with their inverted diagonal blocks."""
 
-    def __init__(self, ops, spec: KernelSpec, frame, Cprep, penalty: float, pc_eps: float):
+    def __init__(self, ops, spec: KernelSpec, frame, Cprep, penalty: float, pc_eps: float, comm=None):
         M = Cprep.n
         Mp = (M + TILE - 1) // TILE * TILE
         self.ops, self.M, self.Mp = ops, M, Mp
@@ -76,8 +76,16 @@ class Preconditioner:
         self.info = ops.zeros(2, dtype=torch.int32)
         ops.potrf(self.L, self.L_inv, self.info[0:1])
         # A A^T ... : G = L^T L / M + lambda I  (= T T^T / M + lambda I), then its Cholesky factor
-        G = ops.empty(Mp, Mp)
-        ops.ltl(self.L, G, 1.0 / M, penalty)
+        if comm is not None and comm.enabled and comm.world > 1 and getattr(ops, "ltl_sharded", False):
+            # L^T L has no sequential chain: every rank forms its share of the 512-row slabs and the
+            # parts are summed over NVLink (the all-reduce result is identical on all ranks)
+            G = ops.zeros(Mp, Mp)
+            ops.ltl(self.L, G, 1.0 / M, 0.0, comm.rank, comm.world)
+            comm.all_reduce(G)
+            ops.add_diag(G, Mp, penalty)
+        else:
+            G = ops.empty(Mp, Mp)
+            ops.ltl(self.L, G, 1.0 / M, penalty)
         self.LA = G
         self.LA_inv = ops.empty(nblk, TILE, TILE)
         ops.potrf(self.LA, self.LA_inv, self.info[1:2])
@@ -203,7 +211,7 @@ class FalkonSolver:
 
             helper = threading.Thread(target=_stage, name="sobolev-b200-staging")
             helper.start()
-        self.pre = pre = Preconditioner(ops, self.spec, self.frame, self.Cprep, self.penalty, self.pc_eps)
+        self.pre = pre = Preconditioner(ops, self.spec, self.frame, self.Cprep, self.penalty, self.pc_eps, self.comm)
         Mp = pre.Mp
         if overlap:
             ev[1].record(main)

@@ -406,6 +406,28 @@ def test_paired_solves_match_two_single_solves(cuda_ops, M, dp):
             assert relerr(pb, xb.double()) < FP32_TOL
 
 
+def test_ltl_parts_sum_to_the_whole(cuda_ops, monkeypatch):
+    """sa_ltl_part: the shares of 3 'ranks' (slabs dealt out cyclically) add up to sa_ltl's G."""
+    from sobolev_alignment_b200 import _native as nat
+
+    monkeypatch.setenv("SAB_CHOL_NB", "256")      # 8 slabs at M = 2048
+    M = 2048
+    g = torch.Generator(device="cuda").manual_seed(2)
+    Z = torch.randn(M, 24, device="cuda", generator=g)
+    A = torch.cdist(Z, Z).mul_(-1.0 / 6.0).exp_()
+    A.diagonal().add_(1e-2)
+    inv = torch.empty(M // 128, 128, 128, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    nat.potrf(A, inv, info)
+    whole = torch.empty(M, M, device="cuda")
+    nat.ltl(A, whole, 1.0 / M, 1e-3)
+    parts = torch.zeros(M, M, device="cuda")
+    for r in range(3):
+        nat.ltl(A, parts, 1.0 / M, 0.0, r, 3)
+    nat.add_diag(parts, M, 1e-3)
+    assert relerr(torch.tril(parts), torch.tril(whole).double()) < 1e-6
+
+
 def test_large_factorisation_and_chained_solves(cuda_ops):
     """
     M = 24 576 = 192 blocks: more CTAs than SMs in the single-launch triangular solve (late blocks start
