@@ -17,6 +17,36 @@ from ..solver import Comm, FalkonSolver, Predictor
 from .options import FalkonOptions
 
 
+class _HostFetch:
+    """Device -> host copy of a tensor on its own stream and thread, overlapped with whatever the caller enqueues."""
+
+    def __init__(self, t: torch.Tensor):
+        import threading
+
+        self._out, self._err = None, None
+        main = torch.cuda.current_stream(t.device)
+        side = torch.cuda.Stream(t.device)
+        side.wait_stream(main)          # the tensor is complete on the caller's stream
+        t.record_stream(side)
+
+        def run():
+            try:
+                torch.cuda.set_device(t.device)
+                with torch.cuda.stream(side):
+                    self._out = t.to("cpu")
+            except BaseException as exc:  # noqa: BLE001 - re-raised by result()
+                self._err = exc
+
+        self._thread = threading.Thread(target=run, name="sobolev-b200-fetch")
+        self._thread.start()
+
+    def result(self) -> torch.Tensor:
+        self._thread.join()
+        if self._err is not None:
+            raise self._err
+        return self._out
+
+
 class Falkon:
     def __init__(self, kernel, penalty: float, M: int, center_selection="uniform", maxiter: int = 20,
                  seed=None, error_fn=None, error_every=1, weight_fn=None, options: FalkonOptions | None = None):
@@ -79,6 +109,11 @@ class Falkon:
             idx = self._select_centres(n_local)
             centres = X[torch.from_numpy(idx).to(X.device)]
             n_total = n_local
+        # Row-sharded fit from host inputs: `ny_points_` has to be a host tensor again (anchors() contract).
+        # Its 600 MB read-back (C3) runs on a helper thread / side stream while the solver works.
+        fetch = None
+        if centres.is_cuda and not X.is_cuda:
+            fetch = _HostFetch(centres)
         solver = FalkonSolver(ops, self.kernel.spec(), self.penalty, self.maxiter, pc_eps=opt.pc_eps(),
                               cg_eps=float(opt.cg_epsilon_32), cg_tol=float(opt.cg_tolerance),
                               full_grad_every=int(opt.cg_full_gradient_every), comm=comm)
@@ -87,7 +122,10 @@ class Falkon:
                               "n_iter": solver.n_iter_, "n_kmv": solver.n_kmv_, "n_total": n_total}
         solver.release()
         self.alpha_ = alpha.to(Y.dtype) if X.is_cuda else alpha.to(Y.dtype).cpu()
-        self.ny_points_ = centres if centres.device == X.device else centres.to(X.device)
+        if fetch is not None:
+            self.ny_points_ = fetch.result()
+        else:
+            self.ny_points_ = centres if centres.device == X.device else centres.to(X.device)
         self.fit_times_ = [time.perf_counter() - t0]
         self._predictor = None
         if self.error_fn is not None and Xts is not None and Yts is not None:
