@@ -72,7 +72,8 @@ class CudaOps:
     def staging_stream(self):
         """Side stream on which host inputs are copied / prepared while the main stream builds the preconditioner."""
         if self._side is None:
-            self._side = torch.cuda.Stream(self.device)
+            # high priority: its short copy / prep kernels go first whenever a preconditioner launch ends
+            self._side = torch.cuda.Stream(self.device, priority=-1)
         return self._side
 
     # ------------------------------------------------------------------ memory plumbing
