@@ -85,6 +85,9 @@ _SIGNATURES = {
     "sa_trsm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64]),
     "sa_trsm_pair": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                              c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int64]),
+    "sa_trsm_premul": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "sa_trsm_pair_w": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                               c_int64, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int64]),
     "sa_coldot": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "sa_cg_update": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_float, c_void_p]),
@@ -338,8 +341,20 @@ def trsm(L: torch.Tensor, invdiag: torch.Tensor, B: torch.Tensor, transpose: boo
     return B
 
 
+def trsm_premul(L: torch.Tensor, invdiag: torch.Tensor) -> torch.Tensor:
+    """Pre-multiplied sub-diagonal tiles [M/128 x 2 x 128 x 128] of a factor (sa_trsm_premul)."""
+    _req(L, torch.float32, "L")
+    _req(invdiag, torch.float32, "invdiag")
+    nblk = L.shape[0] // TILE
+    W = torch.empty(nblk, 2, TILE, TILE, dtype=torch.float32, device=L.device)
+    _check(load().sa_trsm_premul(_stream(), L.data_ptr(), L.shape[0], L.stride(0), invdiag.data_ptr(), W.data_ptr()))
+    STATS.launches += 1
+    return W
+
+
 def trsm_pair(La: torch.Tensor, inva: torch.Tensor, Lb: torch.Tensor, invb: torch.Tensor, Xa: torch.Tensor,
-              Xb: torch.Tensor, V: torch.Tensor | None, lam: float, transpose: bool):
+              Xb: torch.Tensor, V: torch.Tensor | None, lam: float, transpose: bool,
+              Wa: torch.Tensor | None = None, Wb: torch.Tensor | None = None):
     """Xa <- op(La)^-1 Xa ;  Xb <- op(Lb)^-1 (Xa + lam V)   -- two pipelined chained solves in one launch."""
     _req(La, torch.float32, "La")
     _req(Lb, torch.float32, "Lb")
@@ -357,9 +372,11 @@ def trsm_pair(La: torch.Tensor, inva: torch.Tensor, Lb: torch.Tensor, invb: torc
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
     ws = _workspace(Xa.device, int(load().sa_trsm_workspace_bytes(m)))
-    _check(load().sa_trsm_pair(_stream(), La.data_ptr(), La.stride(0), inva.data_ptr(), Lb.data_ptr(), Lb.stride(0),
-                               invb.data_ptr(), m, Xa.data_ptr(), Xb.data_ptr(), _ptr(V), float(lam), Xa.shape[1],
-                               int(transpose), ws.data_ptr(), ws.numel()))
+    if (Wa is None) != (Wb is None):
+        raise ValueError("pre-multiplied tiles must be given for both factors or for none")
+    _check(load().sa_trsm_pair_w(_stream(), La.data_ptr(), La.stride(0), inva.data_ptr(), _ptr(Wa), Lb.data_ptr(),
+                                 Lb.stride(0), invb.data_ptr(), _ptr(Wb), m, Xa.data_ptr(), Xb.data_ptr(), _ptr(V),
+                                 float(lam), Xa.shape[1], int(transpose), ws.data_ptr(), ws.numel()))
     if ev is not None:
         ev[1].record()
         STATS.trsm_events.append((2 * m * (m + TILE) / 2 * 4.0, ev[0], ev[1]))   # both triangles are read once

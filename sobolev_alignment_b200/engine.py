@@ -161,6 +161,7 @@ class CudaOps:
     add_diag = staticmethod(nat.add_diag)
     trsm = staticmethod(nat.trsm)
     trsm_pair = staticmethod(nat.trsm_pair)
+    trsm_premul = staticmethod(nat.trsm_premul)
     coldot = staticmethod(nat.coldot)
     cg_update = staticmethod(nat.cg_update)
     cg_direction = staticmethod(nat.cg_direction)

@@ -89,6 +89,10 @@ class Preconditioner:
         self.LA = G
         self.LA_inv = ops.empty(nblk, TILE, TILE)
         ops.potrf(self.LA, self.LA_inv, self.info[1:2])
+        # pre-multiplied sub-diagonal tiles: one tile product per chain step instead of two
+        premul = getattr(ops, "trsm_premul", None)
+        self.L_w = premul(self.L, self.L_inv) if premul is not None else None
+        self.LA_w = premul(self.LA, self.LA_inv) if premul is not None else None
 
     def check(self):
         info = self.ops.to_host(self.info).tolist()
@@ -116,7 +120,7 @@ class Preconditioner:
         """v <- A^-1 v (in place);  z <- T^-1 v."""
         pair = getattr(self.ops, "trsm_pair", None)
         if pair is not None:
-            return pair(self.LA, self.LA_inv, self.L, self.L_inv, v, z, None, 0.0, True)
+            return pair(self.LA, self.LA_inv, self.L, self.L_inv, v, z, None, 0.0, True, self.LA_w, self.L_w)
         self.invA(v)
         z.copy_(v)
         return self.invT(z)
@@ -125,7 +129,7 @@ class Preconditioner:
         """w <- T^-T w (in place);  out <- A^-T (w + lam v)."""
         pair = getattr(self.ops, "trsm_pair", None)
         if pair is not None:
-            return pair(self.L, self.L_inv, self.LA, self.LA_inv, w, out, v, lam, False)
+            return pair(self.L, self.L_inv, self.LA, self.LA_inv, w, out, v, lam, False, self.L_w, self.LA_w)
         self.invTt(w)
         out.copy_(w)
         if v is not None:

@@ -404,6 +404,11 @@ def test_paired_solves_match_two_single_solves(cuda_ops, M, dp):
             nat.trsm_pair(La, ia, Lb, ib, pa, pb, Vt, lam, tr)
             assert torch.equal(pa, xa)                 # same arithmetic, same order: bit identical
             assert relerr(pb, xb.double()) < FP32_TOL
+            # with the pre-multiplied sub-diagonal tiles (x_c = inv (b - S) - W x_{c-1}: another rounding order)
+            wa, wb = nat.trsm_premul(La, ia), nat.trsm_premul(Lb, ib)
+            qa, qb = B.clone(), torch.full_like(B, float("nan"))
+            nat.trsm_pair(La, ia, Lb, ib, qa, qb, Vt, lam, tr, wa, wb)
+            assert relerr(qa, xa.double()) < FP32_TOL and relerr(qb, xb.double()) < FP32_TOL
 
 
 def test_ltl_parts_sum_to_the_whole(cuda_ops, monkeypatch):

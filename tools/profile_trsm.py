@@ -28,3 +28,9 @@ for tr in (False, True, False, True):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); nat.trsm_pair(A, invd, G, invg, Xa, Xb, None, 0.0, tr); e1.record(); torch.cuda.synchronize()
     print(f"trsm_pair trans={tr}: {e0.elapsed_time(e1):.3f} ms")
+wa, wg = nat.trsm_premul(A, invd), nat.trsm_premul(G, invg)
+torch.cuda.synchronize()
+for tr in (False, True, False, True):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); nat.trsm_pair(A, invd, G, invg, Xa, Xb, None, 0.0, tr, wa, wg); e1.record(); torch.cuda.synchronize()
+    print(f"trsm_pair with pre-multiplied tiles trans={tr}: {e0.elapsed_time(e1):.3f} ms")
