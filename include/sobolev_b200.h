@@ -154,11 +154,12 @@ int sa_trsm_pair(void* stream, const float* La, int64_t lda, const float* inva, 
                  float lambda, int dp, int transpose, void* workspace, int64_t workspace_bytes);
 
 /*
- * Pre-multiplied sub-diagonal tiles of a factor: W [M/128 x 2 x 128 x 128] floats,
+ * Pre-multiplied sub-diagonal tiles of a factor: W = sa_trsm_premul_floats(M) floats, [M/128 x 2 x 128 x 128] tiles
  *   W[c][0] = inv(L_cc) L(c, c-1)   (forward solves)      W[c][1] = L(c+1, c) inv(L_cc)   (backward solves).
  * With them (sa_trsm_pair_w) the block that was just published -- the last dependency of the next block --
  * costs ONE tile product on the chain instead of two.  Wa / Wb may be NULL (then as sa_trsm_pair).
  */
+int64_t sa_trsm_premul_floats(int64_t M); /* size of W in floats: the tiles + 64 (operand scales of the fp16 tile products) */
 int sa_trsm_premul(void* stream, const float* L, int64_t M, int64_t ldl, const float* invdiag, float* W);
 int sa_trsm_pair_w(void* stream, const float* La, int64_t lda, const float* inva, const float* Wa,
                    const float* Lb, int64_t ldb, const float* invb, const float* Wb, int64_t M, float* Xa,

@@ -85,6 +85,7 @@ _SIGNATURES = {
     "sa_trsm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64]),
     "sa_trsm_pair": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                              c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int64]),
+    "sa_trsm_premul_floats": (c_int64, [c_int64]),
     "sa_trsm_premul": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "sa_trsm_pair_w": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                c_int64, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int64]),
@@ -345,10 +346,9 @@ def trsm_premul(L: torch.Tensor, invdiag: torch.Tensor) -> torch.Tensor:
     """Pre-multiplied sub-diagonal tiles [M/128 x 2 x 128 x 128] of a factor (sa_trsm_premul)."""
     _req(L, torch.float32, "L")
     _req(invdiag, torch.float32, "invdiag")
-    nblk = L.shape[0] // TILE
-    W = torch.empty(nblk, 2, TILE, TILE, dtype=torch.float32, device=L.device)
+    W = torch.empty(int(load().sa_trsm_premul_floats(L.shape[0])), dtype=torch.float32, device=L.device)
     _check(load().sa_trsm_premul(_stream(), L.data_ptr(), L.shape[0], L.stride(0), invdiag.data_ptr(), W.data_ptr()))
-    STATS.launches += 1
+    STATS.launches += 5
     return W
 
 

@@ -417,6 +417,114 @@ __device__ __forceinline__ void tile_times_rhs(const float* Ts, const float* xs,
     for (int i = 0; i < 4; ++i) acc[nb][i] += c1[nb][i] + c2[nb][i];
 }
 
+// ---- fp16 hi/lo tile product (half the MMAs of the 3xTF32 form; the chained solve is bound by their throughput)
+// x is converted ONCE per block into packed fp16 pairs, transposed to [column][k] so that a B fragment is one
+// 32-bit shared load; the tile is split in registers.  Scales are powers of two: the tile by `tscale` (from
+// the largest entry of the whole factor / inverse blocks), x by the block's own largest entry.
+constexpr int XH_LD = TS + 8;  // halves per column of the converted x (bank-conflict free fragment loads)
+
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_h2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Converts the x block in xs [128][LX] (fp32) into xh / xl [NB8*8][XH_LD] (fp16 hi / lo of x * 2^e) and returns
+// 2^-e.  Block-wide: contains two __syncthreads; `red` is 8 floats of shared scratch.
+template <int NB8>
+__device__ __forceinline__ float convert_x(const float* xs, __half* xh, __half* xl, float* red) {
+  constexpr int LX = trsm_ldx(NB8);
+  constexpr int NC = NB8 * 8;
+  float m = 0.f;
+  for (int idx = threadIdx.x; idx < TS * NC; idx += 256) m = fmaxf(m, fabsf(xs[(idx / NC) * LX + idx % NC]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  int e = 0;
+  if (m > 0.f && isfinite(m)) frexpf(m, &e);       // m = f 2^e, f in [0.5, 1)
+  const float sc = ldexpf(1.f, 12 - e), inv = ldexpf(1.f, e - 12);
+  for (int idx = threadIdx.x; idx < TS * NC; idx += 256) {
+    const int k = idx / NC, c = idx % NC;
+    const float v = xs[k * LX + c] * sc;
+    const __half h = __float2half_rn(v);
+    xh[c * XH_LD + k] = h;
+    xl[c * XH_LD + k] = __float2half_rn(v - __half2float(h));
+  }
+  __syncthreads();
+  return inv;
+}
+
+// acc = (Ts x) with Ts scaled by tscale (power of two) and x given as the converted hi / lo halves; the caller
+// multiplies by 1 / (tscale * 2^e).  Same fragment ownership as tile_times_rhs.
+template <int NB8, bool TRANS>
+__device__ __forceinline__ void tile_times_xh(const float* Ts, const __half* xh, const __half* xl, float tscale,
+                                              float (&acc)[NB8][4]) {
+  constexpr int LT = trsm_ldt(TRANS);
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = (threadIdx.x >> 5) * 16;
+  float c1[NB8][4];
+#pragma unroll
+  for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[nb][i] = c1[nb][i] = 0.f;
+#pragma unroll 2
+  for (int k0 = 0; k0 < TS; k0 += 16) {
+    // A fragment (m16 x k16): a0 (row g, k 2t..2t+1), a1 (row g+8, same k), a2 / a3: k + 8
+    float v[4][2];
+    if (TRANS) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int k = k0 + 2 * t + 8 * h + q;
+          v[2 * h][q] = Ts[k * LT + m0 + g];
+          v[2 * h + 1][q] = Ts[k * LT + m0 + g + 8];
+        }
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float2 r0 = *reinterpret_cast<const float2*>(Ts + (m0 + g) * LT + k0 + 2 * t + 8 * h);
+        const float2 r1 = *reinterpret_cast<const float2*>(Ts + (m0 + g + 8) * LT + k0 + 2 * t + 8 * h);
+        v[2 * h][0] = r0.x; v[2 * h][1] = r0.y;
+        v[2 * h + 1][0] = r1.x; v[2 * h + 1][1] = r1.y;
+      }
+    }
+    uint32_t ahi[4], alo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_h2(v[i][0] * tscale, v[i][1] * tscale, ahi[i], alo[i]);
+#pragma unroll
+    for (int nb = 0; nb < NB8; ++nb) {
+      const int col = nb * 8 + g;
+      uint32_t bhi[2], blo[2];
+      bhi[0] = *reinterpret_cast<const uint32_t*>(xh + col * XH_LD + k0 + 2 * t);
+      bhi[1] = *reinterpret_cast<const uint32_t*>(xh + col * XH_LD + k0 + 2 * t + 8);
+      blo[0] = *reinterpret_cast<const uint32_t*>(xl + col * XH_LD + k0 + 2 * t);
+      blo[1] = *reinterpret_cast<const uint32_t*>(xl + col * XH_LD + k0 + 2 * t + 8);
+      mma_f16(acc[nb], ahi, bhi);
+      mma_f16(c1[nb], alo, bhi);
+      mma_f16(c1[nb], ahi, blo);
+    }
+  }
+#pragma unroll
+  for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[nb][i] += c1[nb][i];
+}
+
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
                    static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
@@ -580,6 +688,7 @@ struct TrsmJob {
   const float* V;    // optional additive term of the rhs (NULL = none)
   float lambda;
   const float* W;    // optional pre-multiplied sub-diagonal tiles from sa_trsm_premul (NULL = none)
+  const float* scales;  // behind the W tiles: power-of-two operand scales {L, inverse blocks, W} of the fp16 product
 };
 struct TrsmJobs {
   TrsmJob job[2];
@@ -826,7 +935,7 @@ trsm_premul_kernel(const float* __restrict__ L, long long ldl, const float* __re
 
 // Chained solve with pre-multiplied tiles.  Tile sequence of CTA c: the dependency tiles 0 .. c-2, the
 // inverted diagonal block, W[blk]; a two-slot ring as in trsm_chain_kernel.
-template <int DP, bool TRANS>
+template <int DP, bool TRANS, bool F16>
 __global__ void __launch_bounds__(256)
 trsm_chain_w_kernel(const TrsmJobs jobs, int nblk, int* __restrict__ sync) {
   constexpr int NB8 = (DP + 7) / 8;
@@ -835,7 +944,10 @@ trsm_chain_w_kernel(const TrsmJobs jobs, int nblk, int* __restrict__ sync) {
   extern __shared__ __align__(16) float tsm[];
   float* ring = tsm;                  // [2][128][LT]
   float* xring = tsm + 2 * TS * LT;   // [2][128][LX]
+  __half* xh = reinterpret_cast<__half*>(xring + 2 * TS * LX);   // [NB8*8][XH_LD] converted x (F16 only)
+  __half* xl = xh + NB8 * 8 * XH_LD;
   __shared__ int s_ticket, s_next;
+  __shared__ float s_red[8];
   if (threadIdx.x == 0) s_ticket = atomicAdd(sync, 1);
   __syncthreads();
   const int jid = s_ticket % jobs.njobs;
@@ -923,6 +1035,21 @@ trsm_chain_w_kernel(const TrsmJobs jobs, int nblk, int* __restrict__ sync) {
     for (int i = 0; i < 4; ++i) bfrag[nb][i] = 0.f;
   if (jid == 0) load_rhs();
 
+  // acc = tile * x: fp16 hi/lo m16n8k16 (half the MMAs) or 3xTF32 m16n8k8
+  auto product = [&](const float* Tsm, const float* xsm, int which, float (&acc)[NB8][4]) {
+    if constexpr (F16) {
+      const float ts = __ldg(J.scales + which);
+      const float invx = convert_x<NB8>(xsm, xh, xl, s_red);
+      tile_times_xh<NB8, TRANS>(Tsm, xh, xl, ts, acc);
+      const float r = invx / ts;
+#pragma unroll
+      for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[nb][q] *= r;
+    } else {
+      tile_times_rhs<NB8, TRANS>(Tsm, xsm, acc);
+    }
+  };
   bool have_x = false;  // the x block of the current tile was prefetched by the previous iteration
   for (int i = 0; i < nt; ++i) {
     const int kd = kind_of(i);
@@ -962,7 +1089,7 @@ trsm_chain_w_kernel(const TrsmJobs jobs, int nblk, int* __restrict__ sync) {
       }
       __syncthreads();
       float acc[NB8][4];
-      tile_times_rhs<NB8, TRANS>(ring + (i & 1) * TS * LT, xs, acc);
+      product(ring + (i & 1) * TS * LT, xs, 1, acc);
 #pragma unroll
       for (int nb = 0; nb < NB8; ++nb)
 #pragma unroll
@@ -970,7 +1097,7 @@ trsm_chain_w_kernel(const TrsmJobs jobs, int nblk, int* __restrict__ sync) {
     } else {
       __syncthreads();
       float acc[NB8][4];
-      tile_times_rhs<NB8, TRANS>(ring + (i & 1) * TS * LT, xring + (i & 1) * TS * LX, acc);
+      product(ring + (i & 1) * TS * LT, xring + (i & 1) * TS * LX, kd == DEP ? 0 : 2, acc);
 #pragma unroll
       for (int nb = 0; nb < NB8; ++nb)
 #pragma unroll
@@ -1001,10 +1128,13 @@ constexpr int HDR_FLOATS = 64;  // workspace header: [0] max bits, [1] operand s
 __global__ void absmax_kernel(const float* __restrict__ A, long long M, long long lda, int diag_only,
                               unsigned* __restrict__ maxbits) {
   float m = 0.f;
-  if (diag_only) {
+  if (diag_only == 1) {
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < M;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
       m = fmaxf(m, fabsf(A[i * lda + i]));
+  } else if (diag_only == 2) {  // all `lda` columns of the M rows (a dense M x lda array)
+    for (long long r = blockIdx.x; r < M; r += gridDim.x)
+      for (long long c = threadIdx.x; c < lda; c += blockDim.x) m = fmaxf(m, fabsf(A[r * lda + c]));
   } else {  // lower triangle incl. diagonal, one row per block iteration
     for (long long r = blockIdx.x; r < M; r += gridDim.x)
       for (long long c = threadIdx.x; c <= r; c += blockDim.x) m = fmaxf(m, fabsf(A[r * lda + c]));
@@ -1024,6 +1154,17 @@ __global__ void make_scale_kernel(float* hdr, int take_sqrt) {
   const float sc = ldexpf(1.f, 13 - e);
   hdr[1] = sc;
   hdr[2] = 1.f / (sc * sc);
+}
+
+// scales[i] = 2^(12 - e_i) with max_i = f 2^e_i the largest magnitude found by absmax (bits at scales[8 + i])
+__global__ void trsm_scales_kernel(float* scales) {
+  const int i = threadIdx.x;
+  if (i < 3) {
+    const float m = __uint_as_float(reinterpret_cast<unsigned*>(scales)[8 + i]);
+    int e = 0;
+    if (m > 0.f && isfinite(m)) frexpf(m, &e);
+    scales[i] = ldexpf(1.f, 12 - e);
+  }
 }
 
 // fp32 operand -> K-concatenated fp16 pairs, W = K extent of the fp32 operand (multiple of 64):
@@ -1223,15 +1364,20 @@ static int trsm_chain_launch(cudaStream_t st, const TrsmJobs& jobs, long long M,
   bool premul = true;
   for (int j = 0; j < jobs.njobs; ++j) premul = premul && jobs.job[j].W != nullptr;
   if (premul) {
-    if (transpose) {
-      auto kern = trsm_chain_w_kernel<DP, true>;
-      SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      kern<<<nblk * jobs.njobs, 256, smem, st>>>(jobs, nblk, sync);
-    } else {
-      auto kern = trsm_chain_w_kernel<DP, false>;
-      SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      kern<<<nblk * jobs.njobs, 256, smem, st>>>(jobs, nblk, sync);
-    }
+    // fp16 hi/lo tile products (half the MMAs) measured only 10 % faster than 3xTF32 -- the conversion of x and
+    // the register split of the tile eat the saving -- so the TF32 form stays the default
+    const char* tv = std::getenv("SAB_TRSM_F16");
+    const bool f16 = tv && std::atoi(tv) != 0;
+    const int smem_w = smem + (f16 ? 2 * ((DP + 7) / 8) * 8 * XH_LD * static_cast<int>(sizeof(__half)) : 0);
+    auto go = [&](auto kern) -> int {
+      SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w));
+      kern<<<nblk * jobs.njobs, 256, smem_w, st>>>(jobs, nblk, sync);
+      return 0;
+    };
+    int rc;
+    if (transpose) rc = f16 ? go(trsm_chain_w_kernel<DP, true, true>) : go(trsm_chain_w_kernel<DP, true, false>);
+    else rc = f16 ? go(trsm_chain_w_kernel<DP, false, true>) : go(trsm_chain_w_kernel<DP, false, false>);
+    if (rc) return rc;
   } else if (transpose) {
     auto kern = trsm_chain_kernel<DP, true>;
     SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1253,7 +1399,7 @@ static int trsm_launch(cudaStream_t st, const float* L, long long M, long long l
   if (sync != nullptr && !(ev && std::atoi(ev) != 0)) {
     TrsmJobs jobs = {};
     jobs.njobs = 1;
-    jobs.job[0] = TrsmJob{L, ldl, invdiag, B, B, nullptr, 0.f, W};
+    jobs.job[0] = TrsmJob{L, ldl, invdiag, B, B, nullptr, 0.f, W, W ? W + (M / TS) * 2ll * TS * TS : nullptr};
     {
       const char* tp = std::getenv("SAB_TRSM_TRACE_PTR");
       jobs.trace = tp ? reinterpret_cast<long long*>(std::strtoull(tp, nullptr, 0)) : nullptr;
@@ -1473,14 +1619,29 @@ static int trsm_pair_dp(cudaStream_t st, const TrsmJobs& jobs, long long M, int 
   return trsm_chain_launch<DP>(st, jobs, M, transpose, sync);
 }
 
+extern "C" int64_t sa_trsm_premul_floats(int64_t M) {
+  return M <= 0 ? -1 : (M / TS) * 2 * static_cast<int64_t>(TS) * TS + 64;
+}
+
 extern "C" int sa_trsm_premul(void* stream, const float* L, int64_t M, int64_t ldl, const float* invdiag,
                               float* W) {
   SAB_REQUIRE_MAT(M, ldl, L);
   SAB_REQUIRE(invdiag != nullptr && W != nullptr && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "bad operands");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nblk = static_cast<int>(M / TS);
   const int smem = (TS * PM_LDA + TS * TS) * static_cast<int>(sizeof(float));
   SAB_CHECK_CUDA(cudaFuncSetAttribute(trsm_premul_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  trsm_premul_kernel<<<dim3(nblk, 2), 256, smem, static_cast<cudaStream_t>(stream)>>>(L, ldl, invdiag, nblk, W);
+  trsm_premul_kernel<<<dim3(nblk, 2), 256, smem, st>>>(L, ldl, invdiag, nblk, W);
+  // power-of-two scales of the fp16 tile products behind the tiles: {L, inverted diagonal blocks, W}
+  const long long tiles = static_cast<long long>(nblk) * 2 * TS * TS;
+  float* scales = W + tiles;
+  SAB_CHECK_CUDA(cudaMemsetAsync(scales, 0, 64 * sizeof(float), st));
+  unsigned* bits = reinterpret_cast<unsigned*>(scales) + 8;
+  absmax_kernel<<<1184, 256, 0, st>>>(L, M, ldl, 0, bits + 0);
+  absmax_kernel<<<static_cast<int>(ceil_div(static_cast<long long>(nblk) * TS, 8)), 256, 0, st>>>(
+      invdiag, static_cast<long long>(nblk) * TS, TS, 2, bits + 1);
+  absmax_kernel<<<static_cast<int>(ceil_div(2ll * nblk * TS, 8)), 256, 0, st>>>(W, 2ll * nblk * TS, TS, 2, bits + 2);
+  trsm_scales_kernel<<<1, 32, 0, st>>>(scales);
   SAB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1498,8 +1659,9 @@ extern "C" int sa_trsm_pair_w(void* stream, const float* La, int64_t lda, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TrsmJobs jobs = {};
   jobs.njobs = 2;
-  jobs.job[0] = TrsmJob{La, lda, inva, Xa, Xa, nullptr, 0.f, Wa};
-  jobs.job[1] = TrsmJob{Lb, ldb, invb, Xa, Xb, V, lambda, Wb};
+  const long long tiles = (M / TS) * 2ll * TS * TS;
+  jobs.job[0] = TrsmJob{La, lda, inva, Xa, Xa, nullptr, 0.f, Wa, Wa ? Wa + tiles : nullptr};
+  jobs.job[1] = TrsmJob{Lb, ldb, invb, Xa, Xb, V, lambda, Wb, Wb ? Wb + tiles : nullptr};
   int* sync = static_cast<int*>(workspace);
   switch (dp) {
     case 4: return trsm_pair_dp<4>(st, jobs, M, transpose, sync);

@@ -376,7 +376,7 @@ def test_cholesky_ltl_trsm(cuda_ops, M, dp, nb, monkeypatch):
 
 
 @pytest.mark.parametrize("M,dp", [(128, 4), (1024, 20), (4096, 12)])
-def test_paired_solves_match_two_single_solves(cuda_ops, M, dp):
+def test_paired_solves_match_two_single_solves(cuda_ops, M, dp, monkeypatch):
     """sa_trsm_pair (two pipelined chains in one launch) against two sa_trsm calls, both directions, with the lambda V term."""
     from sobolev_alignment_b200 import _native as nat
 
@@ -406,9 +406,12 @@ def test_paired_solves_match_two_single_solves(cuda_ops, M, dp):
             assert relerr(pb, xb.double()) < FP32_TOL
             # with the pre-multiplied sub-diagonal tiles (x_c = inv (b - S) - W x_{c-1}: another rounding order)
             wa, wb = nat.trsm_premul(La, ia), nat.trsm_premul(Lb, ib)
-            qa, qb = B.clone(), torch.full_like(B, float("nan"))
-            nat.trsm_pair(La, ia, Lb, ib, qa, qb, Vt, lam, tr, wa, wb)
-            assert relerr(qa, xa.double()) < FP32_TOL and relerr(qb, xb.double()) < FP32_TOL
+            for f16 in ("0", "1"):                      # 3xTF32 (default) and fp16 hi/lo tile products
+                monkeypatch.setenv("SAB_TRSM_F16", f16)
+                qa, qb = B.clone(), torch.full_like(B, float("nan"))
+                nat.trsm_pair(La, ia, Lb, ib, qa, qb, Vt, lam, tr, wa, wb)
+                assert relerr(qa, xa.double()) < FP32_TOL and relerr(qb, xb.double()) < FP32_TOL
+            monkeypatch.delenv("SAB_TRSM_F16")
 
 
 def test_ltl_parts_sum_to_the_whole(cuda_ops, monkeypatch):
