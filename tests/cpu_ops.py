@@ -72,6 +72,17 @@ class CpuOps:
         B.copy_(torch.linalg.solve_triangular(Lt.T if transpose else Lt, B, upper=bool(transpose)))
         return B
 
+    def trsm_premul(self, L, invdiag):
+        return "premul-token"          # the CUDA engine returns the pre-multiplied tiles; the stand-in needs none
+
+    def trsm_pair(self, La, inva, Lb, invb, Xa, Xb, V, lam, transpose, Wa=None, Wb=None):
+        """Xa <- op(La)^-1 Xa ; Xb <- op(Lb)^-1 (Xa + lam V)  (same contract as _native.trsm_pair)."""
+        assert (Wa is None) == (Wb is None)
+        self.trsm(La, inva, Xa, transpose)
+        Xb.copy_(Xa if V is None else Xa + lam * V)
+        self.trsm(Lb, invb, Xb, transpose)
+        return Xb
+
     def coldot(self, P, Q, out):
         out.copy_((P * Q).sum(0))
         return out
