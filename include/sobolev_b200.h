@@ -42,6 +42,11 @@ enum {
 int sa_version(void);
 const char* sa_last_error(void);
 
+/* Tuning / diagnostic options, e.g. sa_set_option("SAB_TRSM_CHUNK", "32").  The
+ * SAB_* environment variable of the same name is the default, read once at its first use; value NULL
+ * restores it.  Not on the reference's path. */
+int sa_set_option(const char* name, const char* value);
+
 /* Number of SMs / bytes of dynamic shared memory the fused kernel was configured with for the
  * current device (diagnostics for bench.py). */
 int sa_device_info(int* sm_count, int* smem_bytes);
@@ -132,53 +137,67 @@ int sa_add_diag(void* stream, float* A, int64_t M, int64_t lda, float value);
 
 /*
  * Triangular solves with a Cholesky factor from sa_potrf (cuBLAS `trsm` inside falkon's
- * `invT / invTt / invA / invAt` [ext]):  B[M x dp] <- L^-1 B (transpose = 0) or L^-T B (transpose = 1).
- * One launch per solve; the block-to-block dependencies run through flags in `workspace` (caller-owned
- * scratch of at least sa_trsm_workspace_bytes(M) bytes, 16-byte aligned; zeroed by the library on the
- * same stream).
+ * `invT / invTt / invA / invAt` [ext], 4 per CG iteration of the fit at krr_approx.py:227).
+ *
+ * The factor is constant over the ~90 solves of a fit, so it is PACKED once: every strictly-lower
+ * 128 x 128 tile, the inverted diagonal blocks and the pre-multiplied sub-diagonal tiles
+ * inv(L_cc) L(c, c-1) / L(c+1, c) inv(L_cc) as fp16 pairs (x 2^s = hi + lo: the bytes of fp32, ~22 bits)
+ * in the shared-memory image of the solve kernel.  `packed` is caller-owned, sa_trsm_packed_bytes(M) bytes
+ * (about HALF of the fp32 square, which may be released afterwards), 128-byte aligned;
+ * `workspace` of sa_trsm_pack holds sa_trsm_pack_workspace_bytes(M) bytes (fp32 staging of the
+ * pre-multiplied tiles).
+ */
+int64_t sa_trsm_packed_bytes(int64_t M);
+int64_t sa_trsm_pack_workspace_bytes(int64_t M);
+int sa_trsm_pack(void* stream, const float* L, int64_t M, int64_t ldl, const float* invdiag, void* packed,
+                 void* workspace, int64_t workspace_bytes);
+
+/*
+ * B[M x dp] <- L^-1 B (transpose = 0) or L^-T B (transpose = 1) with a packed factor.  One persistent
+ * launch per solve: block rows are cut into chunks of dependency tiles that CTAs draw from a ticket, the
+ * block-to-block chain runs through flags in `workspace` (caller-owned scratch of at least
+ * sa_trsm_workspace_bytes(M) bytes, 128-byte aligned; the flags are zeroed by the library on the same
+ * stream).  Sums are formed in a fixed order: results are bit-reproducible.
  */
 int64_t sa_trsm_workspace_bytes(int64_t M);
-int sa_trsm(void* stream, const float* L, int64_t M, int64_t ldl, const float* invdiag, float* B,
-            int dp, int transpose, void* workspace, int64_t workspace_bytes);
+int sa_trsm_solve(void* stream, const void* packed, int64_t M, float* B, int dp, int transpose,
+                  void* workspace, int64_t workspace_bytes);
 
 /*
  * Two dependent solves in one launch (the preconditioner is always applied as such a pair: A^-1 then
  * T^-1, and T^-T then A^-T, `FalkonPreconditioner.apply / apply_t` [ext]):
  *   Xa <- op(La)^-1 Xa                       (in place)
  *   Xb <- op(Lb)^-1 (Xa + lambda * V)        (V may be NULL)
- * op = identity (transpose = 0) or transposition (1) for both.  The second chain starts block c as soon
+ * op = identity (transpose = 0) or transposition (1) for both.  The second chain takes block c as soon
  * as the first has published it, so the pair costs one chain latency.  Xa != Xb; same workspace contract.
  */
-int sa_trsm_pair(void* stream, const float* La, int64_t lda, const float* inva, const float* Lb,
-                 int64_t ldb, const float* invb, int64_t M, float* Xa, float* Xb, const float* V,
-                 float lambda, int dp, int transpose, void* workspace, int64_t workspace_bytes);
-
-/*
- * Pre-multiplied sub-diagonal tiles of a factor: W = sa_trsm_premul_floats(M) floats, [M/128 x 2 x 128 x 128] tiles
- *   W[c][0] = inv(L_cc) L(c, c-1)   (forward solves)      W[c][1] = L(c+1, c) inv(L_cc)   (backward solves).
- * With them (sa_trsm_pair_w) the block that was just published -- the last dependency of the next block --
- * costs ONE tile product on the chain instead of two.  Wa / Wb may be NULL (then as sa_trsm_pair).
- */
-int64_t sa_trsm_premul_floats(int64_t M); /* size of W in floats: the tiles + 64 (operand scales of the fp16 tile products) */
-int sa_trsm_premul(void* stream, const float* L, int64_t M, int64_t ldl, const float* invdiag, float* W);
-int sa_trsm_pair_w(void* stream, const float* La, int64_t lda, const float* inva, const float* Wa,
-                   const float* Lb, int64_t ldb, const float* invb, const float* Wb, int64_t M, float* Xa,
-                   float* Xb, const float* V, float lambda, int dp, int transpose, void* workspace,
-                   int64_t workspace_bytes);
+int sa_trsm_solve_pair(void* stream, const void* packed_a, const void* packed_b, int64_t M, float* Xa,
+                       float* Xb, const float* V, float lambda, int dp, int transpose, void* workspace,
+                       int64_t workspace_bytes);
 
 /*
  * Conjugate-gradient vector kernels (falkon `ConjugateGradient.solve` [ext]); all M x dp fp32.
  * sa_coldot:   out[c] = sum_i P[i, c] * Q[i, c]                    (out is overwritten)
  * sa_cg_update: alpha_c = rs_old[c] / (pAp[c] + eps);  X += P alpha;  R -= AP alpha (if AP != NULL);
  *              rs_new[c] = sum_i R[i, c]^2 (if R updated)
- * sa_cg_direction: P = R + (rs_new / rs_old) P
+ * sa_cg_direction: P = R + rs_new / (rs_old + eps) P
  * sa_axpby:    Y = a * X + b * Y   (elementwise, len floats)
+ * Column sums are deterministic (per-block partials in `workspace`, folded in index order by the block
+ * that finishes last; no float atomics), so replicated solver state stays bit-identical across ranks.
+ * `workspace`: sa_cg_workspace_bytes() bytes, zeroed ONCE by the caller before its first use.
+ * Convergence is decided on the device: when `hist` != NULL the sums are also stored to hist[0..dp)
+ * (one row of the residual history); when `stop` != NULL, *stop is raised once max_c sqrt(sum_c) < tol,
+ * and sa_cg_update / sa_cg_direction become no-ops while *stop != 0 (the host reads the flag late,
+ * without synchronising every iteration -- falkon reads the residual every iteration).
  */
-int sa_coldot(void* stream, const float* P, const float* Q, int64_t M, int dp, float* out);
+int64_t sa_cg_workspace_bytes(void);
+int sa_coldot(void* stream, const float* P, const float* Q, int64_t M, int dp, float* out, void* workspace,
+              float* hist, int* stop, float tol);
 int sa_cg_update(void* stream, int64_t M, int dp, const float* P, const float* AP, float* X,
-                 float* R, const float* rs_old, const float* pAp, float eps, float* rs_new);
+                 float* R, const float* rs_old, const float* pAp, float eps, float* rs_new, void* workspace,
+                 float* hist, int* stop, float tol);
 int sa_cg_direction(void* stream, int64_t M, int dp, const float* R, float* P, const float* rs_new,
-                    const float* rs_old);
+                    const float* rs_old, float eps, const int* stop);
 int sa_axpby(void* stream, int64_t len, float a, const float* X, float b, float* Y);
 
 #ifdef __cplusplus

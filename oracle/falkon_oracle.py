@@ -159,7 +159,7 @@ def conjugate_gradient(mmv, B, maxiter, cg_eps=CG_EPSILON_F32, tol=CG_TOLERANCE,
             trace.append(float(rs_new.max().sqrt()))
         if float(rs_new.max().sqrt()) < tol:
             break
-        P = R + P * (rs_new / rs_old)[None, :]
+        P = R + P * (rs_new / (rs_old + cg_eps))[None, :]   # falkon: Rsnew / (Rsold + cg_epsilon)
         rs_old = rs_new
     return X, n_iter
 

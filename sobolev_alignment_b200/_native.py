@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 import torch
@@ -63,6 +64,7 @@ _lib = None
 _SIGNATURES = {
     "sa_version": (c_int, []),
     "sa_last_error": (c_char_p, []),
+    "sa_set_option": (c_int, [c_char_p, c_char_p]),
     "sa_device_info": (c_int, [c_void_p, c_void_p]),
     "sa_prep": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_float,
                         c_void_p, c_int64, c_void_p, c_int64]),
@@ -81,18 +83,20 @@ _SIGNATURES = {
     "sa_ltl_part": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p,
                             c_int64, c_int, c_int]),
     "sa_add_diag": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float]),
+    "sa_trsm_packed_bytes": (c_int64, [c_int64]),
+    "sa_trsm_pack_workspace_bytes": (c_int64, [c_int64]),
+    "sa_trsm_pack": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64]),
     "sa_trsm_workspace_bytes": (c_int64, [c_int64]),
-    "sa_trsm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64]),
-    "sa_trsm_pair": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
-                             c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int64]),
-    "sa_trsm_premul_floats": (c_int64, [c_int64]),
-    "sa_trsm_premul": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
-    "sa_trsm_pair_w": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
-                               c_int64, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int64]),
-    "sa_coldot": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "sa_trsm_solve": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_int64]),
+    "sa_trsm_solve_pair": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_float,
+                                   c_int, c_int, c_void_p, c_int64]),
+    "sa_cg_workspace_bytes": (c_int64, []),
+    "sa_coldot": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_float]),
     "sa_cg_update": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                             c_void_p, c_float, c_void_p]),
-    "sa_cg_direction": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+                             c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_float]),
+    "sa_cg_direction": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                c_void_p]),
     "sa_axpby": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_float, c_void_p]),
 }
 
@@ -120,14 +124,27 @@ def load():
     return _lib
 
 
+def set_option(name: str, value=None):
+    """Tuning / diagnostic option of the library (SAB_*); None restores the environment's value."""
+    _check(load().sa_set_option(name.encode(), None if value is None else str(value).encode()))
+
+
 def _check(rc: int):
     if rc != 0:
         msg = load().sa_last_error()
         raise NativeLibraryError(f"libsobolev_b200 call failed ({rc}): {msg.decode() if msg else '?'}")
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _call(fn, device, *args):
+    """
+    Enqueue a library call on the CURRENT stream of `device` with that device current (the library
+    launches on cudaGetDevice(); the tensors may live on a GPU that is not torch's current one).
+    """
+    if device.index is None or device.index == torch.cuda.current_device():
+        _check(fn(torch.cuda.current_stream(device).cuda_stream, *args))
+        return
+    with torch.cuda.device(device):
+        _check(fn(torch.cuda.current_stream(device).cuda_stream, *args))
 
 
 def _ptr(t: torch.Tensor | None) -> int | None:
@@ -179,8 +196,8 @@ def prep(X: torch.Tensor, shift: torch.Tensor | None, scale: torch.Tensor | None
         norms_len = (out.norms.numel() - row_offset) if last else n
     if n == 0:
         return out
-    _check(lib.sa_prep(_stream(), X.data_ptr(), n, p, X.stride(0), _ptr(shift), _ptr(scale),
-                       float(gscale), dptr, out.p_pad, nptr, norms_len))
+    _call(lib.sa_prep, X.device, X.data_ptr(), n, p, X.stride(0), _ptr(shift), _ptr(scale),
+                       float(gscale), dptr, out.p_pad, nptr, norms_len)
     STATS.launches += 1
     return out
 
@@ -195,13 +212,13 @@ def colstats(X: torch.Tensor, log10p1: bool):
     s2 = torch.zeros(p, dtype=torch.float64, device=X.device)
     # pivot = f(first row): sums of (y - pivot) keep the variance free of cancellation
     pivot = torch.empty(1, p, dtype=torch.float32, device=X.device)
-    _check(lib.sa_transform_rows(_stream(), X.data_ptr(), 1, p, X.stride(0), int(log10p1), None, None, 1.0,
-                                 pivot.data_ptr(), p, None))
+    _call(lib.sa_transform_rows, X.device, X.data_ptr(), 1, p, X.stride(0), int(log10p1), None, None, 1.0,
+                                 pivot.data_ptr(), p, None)
     step = 65535 * 4096
     for r0 in range(0, n, step):
         r1 = min(n, r0 + step)
-        _check(lib.sa_colstats(_stream(), X[r0:r1].data_ptr(), r1 - r0, p, X.stride(0), int(log10p1),
-                               pivot.data_ptr(), s1.data_ptr(), s2.data_ptr()))
+        _call(lib.sa_colstats, X.device, X[r0:r1].data_ptr(), r1 - r0, p, X.stride(0), int(log10p1),
+                               pivot.data_ptr(), s1.data_ptr(), s2.data_ptr())
         STATS.launches += 2
     m = s1 / n
     var = (s2 / n - m * m).clamp_min_(0.0)
@@ -217,8 +234,8 @@ def transform_rows(X: torch.Tensor, log10p1: bool, shift: torch.Tensor | None, s
     n, p = X.shape
     acc = torch.zeros(1, dtype=torch.float64, device=X.device) if want_row_norms else None
     if n:
-        _check(lib.sa_transform_rows(_stream(), X.data_ptr(), n, p, X.stride(0), int(log10p1), _ptr(shift), _ptr(scale),
-                                     float(gain), X.data_ptr(), X.stride(0), _ptr(acc)))
+        _call(lib.sa_transform_rows, X.device, X.data_ptr(), n, p, X.stride(0), int(log10p1), _ptr(shift), _ptr(scale),
+                                     float(gain), X.data_ptr(), X.stride(0), _ptr(acc))
         STATS.launches += 1
     return acc
 
@@ -231,16 +248,22 @@ def alloc_prepared(n: int, p: int, device) -> Prepared:
 
 
 _workspaces = {}
+_workspaces_lock = threading.Lock()
 
 
 def _workspace(device, nbytes: int) -> torch.Tensor:
-    """Scratch for the V pre-pass of sa_kmv, one growing buffer per device (stream-ordered reuse)."""
-    key = (device.type, device.index)
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
-    return ws
+    """
+    Scratch of sa_kmv (V tiles), the Cholesky operand panels and the triangular-solve flags: one growing
+    buffer per (device, stream) -- reuse is ordered by that stream, and work issued from another stream
+    or thread gets a buffer of its own.
+    """
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+    with _workspaces_lock:
+        ws = _workspaces.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            _workspaces[key] = ws
+        return ws
 
 
 def kmv(kernel_id: int, kscale: float, A: Prepared, B: Prepared, V: torch.Tensor, out: torch.Tensor,
@@ -257,16 +280,16 @@ def kmv(kernel_id: int, kscale: float, A: Prepared, B: Prepared, V: torch.Tensor
     ev = None
     if STATS.time_kmv:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        ev[0].record()
+        ev[0].record(torch.cuda.current_stream(V.device))
     nbytes = int(lib.sa_kmv_workspace_bytes(B.n, dp))
     if nbytes < 0:
         raise NativeLibraryError(f"dp must be a multiple of 4 in [4, 32], got {dp}")
     ws = _workspace(V.device, nbytes)
-    _check(lib.sa_kmv(_stream(), kernel_id, float(kscale), A.data.data_ptr(), A.norms.data_ptr(), A.n,
+    _call(lib.sa_kmv, V.device, kernel_id, float(kscale), A.data.data_ptr(), A.norms.data_ptr(), A.n,
                       A.p_pad, B.data.data_ptr(), B.norms.data_ptr(), B.n, B.p_pad, A.p_pad,
-                      V.data_ptr(), dp, out.data_ptr(), int(symmetric), ws.data_ptr(), ws.numel()))
+                      V.data_ptr(), dp, out.data_ptr(), int(symmetric), ws.data_ptr(), ws.numel())
     if ev is not None:
-        ev[1].record()
+        ev[1].record(torch.cuda.current_stream(V.device))
         # algorithmic work: 2 a b p + 2 a b d, with the caller's p and padded d
         STATS.kmv_events.append((2.0 * A.n * B.n * (A.p + dp), ev[0], ev[1]))
     STATS.launches += 3   # column maxima, fp16 split of V, fused kernel
@@ -281,9 +304,9 @@ def kdense(kernel_id: int, kscale: float, A: Prepared, B: Prepared, out: torch.T
         raise NativeLibraryError("kdense output must be a float32 CUDA tensor with unit column stride")
     if out.shape[0] < A.n or out.shape[1] < B.n:
         raise ValueError("output too small")
-    _check(lib.sa_kdense(_stream(), kernel_id, float(kscale), A.data.data_ptr(), A.norms.data_ptr(), A.n,
+    _call(lib.sa_kdense, out.device, kernel_id, float(kscale), A.data.data_ptr(), A.norms.data_ptr(), A.n,
                          A.p_pad, B.data.data_ptr(), B.norms.data_ptr(), B.n, B.p_pad, A.p_pad,
-                         out.data_ptr(), out.stride(0), int(symmetric)))
+                         out.data_ptr(), out.stride(0), int(symmetric))
     STATS.launches += 1
     return out
 
@@ -300,8 +323,8 @@ def potrf(A: torch.Tensor, invdiag: torch.Tensor, info: torch.Tensor):
     _req(A, torch.float32, "A")
     _req(invdiag, torch.float32, "invdiag")
     ws = _linalg_workspace(A.device, A.shape[0])
-    _check(load().sa_potrf(_stream(), A.data_ptr(), A.shape[0], A.stride(0), invdiag.data_ptr(),
-                           info.data_ptr(), ws.data_ptr(), ws.numel()))
+    _call(load().sa_potrf, A.device, A.data_ptr(), A.shape[0], A.stride(0), invdiag.data_ptr(),
+                           info.data_ptr(), ws.data_ptr(), ws.numel())
     nblk = A.shape[0] // TILE
     STATS.launches += 2 + nblk + 3 * (nblk - 1)   # scale, diagonal blocks, (panel, split, update) per step
 
@@ -311,97 +334,148 @@ def ltl(L: torch.Tensor, G: torch.Tensor, alpha: float, beta: float, part: int =
     _req(L, torch.float32, "L")
     _req(G, torch.float32, "G")
     ws = _linalg_workspace(L.device, L.shape[0])
-    _check(load().sa_ltl_part(_stream(), L.data_ptr(), L.shape[0], L.stride(0), G.data_ptr(), G.stride(0),
-                              float(alpha), float(beta), ws.data_ptr(), ws.numel(), int(part), int(nparts)))
+    _call(load().sa_ltl_part, L.device, L.data_ptr(), L.shape[0], L.stride(0), G.data_ptr(), G.stride(0),
+                              float(alpha), float(beta), ws.data_ptr(), ws.numel(), int(part), int(nparts))
     STATS.launches += 3 + 2 * (L.shape[0] // TILE)   # scale, (split, update) per block row, diagonal
 
 
 def add_diag(A: torch.Tensor, m: int, value: float):
     _req(A, torch.float32, "A")
-    _check(load().sa_add_diag(_stream(), A.data_ptr(), m, A.stride(0), float(value)))
+    _call(load().sa_add_diag, A.device, A.data_ptr(), m, A.stride(0), float(value))
     STATS.launches += 1
 
 
-def trsm(L: torch.Tensor, invdiag: torch.Tensor, B: torch.Tensor, transpose: bool):
+class PackedFactor:
+    """Solve-ready form of a Cholesky factor (sa_trsm_pack): fp16 hi/lo tiles + inverse / pre-multiplied blocks."""
+
+    __slots__ = ("data", "m")
+
+    def __init__(self, data: torch.Tensor, m: int):
+        self.data, self.m = data, m
+
+
+def trsm_pack(L: torch.Tensor, invdiag: torch.Tensor) -> PackedFactor:
+    """Pack the lower factor L (fp32 [m x m], m % 128 == 0) for the triangular solves; L may be freed afterwards."""
     _req(L, torch.float32, "L")
+    _req(invdiag, torch.float32, "invdiag")
+    m = L.shape[0]
+    nbytes = int(load().sa_trsm_packed_bytes(m))
+    if nbytes < 0:
+        raise NativeLibraryError("matrix order must be a positive multiple of 128")
+    data = torch.empty(nbytes, dtype=torch.uint8, device=L.device)
+    ws = _workspace(L.device, int(load().sa_trsm_pack_workspace_bytes(m)))
+    _call(load().sa_trsm_pack, L.device, L.data_ptr(), m, L.stride(0), invdiag.data_ptr(), data.data_ptr(),
+          ws.data_ptr(), ws.numel())
+    STATS.launches += 7
+    return PackedFactor(data, m)
+
+
+def _timed(device):
+    if not STATS.time_kmv:
+        return None
+    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ev[0].record(torch.cuda.current_stream(device))
+    return ev
+
+
+def trsm(F: PackedFactor, B: torch.Tensor, transpose: bool):
+    """B <- L^-1 B (transpose False) or L^-T B (True), in place, with a packed factor."""
     _req(B, torch.float32, "B")
-    if B.shape[0] != L.shape[0]:
+    if B.shape[0] != F.m:
         raise ValueError("rhs rows must equal the (padded) matrix order")
-    ev = None
-    if STATS.time_kmv:
-        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        ev[0].record()
-    ws = _workspace(B.device, int(load().sa_trsm_workspace_bytes(L.shape[0])))
-    _check(load().sa_trsm(_stream(), L.data_ptr(), L.shape[0], L.stride(0), invdiag.data_ptr(),
-                          B.data_ptr(), B.shape[1], int(transpose), ws.data_ptr(), ws.numel()))
+    ev = _timed(B.device)
+    ws = _workspace(B.device, int(load().sa_trsm_workspace_bytes(F.m)))
+    _call(load().sa_trsm_solve, B.device, F.data.data_ptr(), F.m, B.data_ptr(), B.shape[1], int(transpose),
+          ws.data_ptr(), ws.numel())
     if ev is not None:
-        ev[1].record()
-        m = L.shape[0]
-        STATS.trsm_events.append((m * (m + TILE) / 2 * 4.0, ev[0], ev[1]))   # the triangle is read once
+        ev[1].record(torch.cuda.current_stream(B.device))
+        STATS.trsm_events.append((F.m * (F.m + TILE) / 2 * 4.0, ev[0], ev[1]))   # the triangle is read once
     STATS.launches += 1
     return B
 
 
-def trsm_premul(L: torch.Tensor, invdiag: torch.Tensor) -> torch.Tensor:
-    """Pre-multiplied sub-diagonal tiles [M/128 x 2 x 128 x 128] of a factor (sa_trsm_premul)."""
-    _req(L, torch.float32, "L")
-    _req(invdiag, torch.float32, "invdiag")
-    W = torch.empty(int(load().sa_trsm_premul_floats(L.shape[0])), dtype=torch.float32, device=L.device)
-    _check(load().sa_trsm_premul(_stream(), L.data_ptr(), L.shape[0], L.stride(0), invdiag.data_ptr(), W.data_ptr()))
-    STATS.launches += 5
-    return W
-
-
-def trsm_pair(La: torch.Tensor, inva: torch.Tensor, Lb: torch.Tensor, invb: torch.Tensor, Xa: torch.Tensor,
-              Xb: torch.Tensor, V: torch.Tensor | None, lam: float, transpose: bool,
-              Wa: torch.Tensor | None = None, Wb: torch.Tensor | None = None):
-    """Xa <- op(La)^-1 Xa ;  Xb <- op(Lb)^-1 (Xa + lam V)   -- two pipelined chained solves in one launch."""
-    _req(La, torch.float32, "La")
-    _req(Lb, torch.float32, "Lb")
+def trsm_pair(Fa: PackedFactor, Fb: PackedFactor, Xa: torch.Tensor, Xb: torch.Tensor, V: torch.Tensor | None,
+              lam: float, transpose: bool):
+    """Xa <- op(La)^-1 Xa ;  Xb <- op(Lb)^-1 (Xa + lam V)   -- two interleaved chained solves in one launch."""
     _req(Xa, torch.float32, "Xa")
     _req(Xb, torch.float32, "Xb")
     if V is not None:
         _req(V, torch.float32, "V")
-    m = La.shape[0]
-    if Lb.shape[0] != m or Xa.shape != Xb.shape or Xa.shape[0] != m or (V is not None and V.shape != Xa.shape):
+    m = Fa.m
+    if Fb.m != m or Xa.shape != Xb.shape or Xa.shape[0] != m or (V is not None and V.shape != Xa.shape):
         raise ValueError("shape mismatch")
     if Xa.data_ptr() == Xb.data_ptr():
         raise ValueError("Xa and Xb must be different buffers")
-    ev = None
-    if STATS.time_kmv:
-        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        ev[0].record()
+    ev = _timed(Xa.device)
     ws = _workspace(Xa.device, int(load().sa_trsm_workspace_bytes(m)))
-    if (Wa is None) != (Wb is None):
-        raise ValueError("pre-multiplied tiles must be given for both factors or for none")
-    _check(load().sa_trsm_pair_w(_stream(), La.data_ptr(), La.stride(0), inva.data_ptr(), _ptr(Wa), Lb.data_ptr(),
-                                 Lb.stride(0), invb.data_ptr(), _ptr(Wb), m, Xa.data_ptr(), Xb.data_ptr(), _ptr(V),
-                                 float(lam), Xa.shape[1], int(transpose), ws.data_ptr(), ws.numel()))
+    _call(load().sa_trsm_solve_pair, Xa.device, Fa.data.data_ptr(), Fb.data.data_ptr(), m, Xa.data_ptr(),
+          Xb.data_ptr(), _ptr(V), float(lam), Xa.shape[1], int(transpose), ws.data_ptr(), ws.numel())
     if ev is not None:
-        ev[1].record()
+        ev[1].record(torch.cuda.current_stream(Xa.device))
         STATS.trsm_events.append((2 * m * (m + TILE) / 2 * 4.0, ev[0], ev[1]))   # both triangles are read once
     STATS.launches += 1
     return Xb
 
 
-def coldot(P: torch.Tensor, Q: torch.Tensor, out: torch.Tensor):
+class CgScratch:
+    """
+    Device scratch of one CG run: reduction slots of the deterministic column sums, the stop flag the
+    kernels raise on convergence, the residual history [maxiter x dp], and pinned slots through which
+    the host reads the flag a few iterations late (no per-iteration synchronisation).
+    """
+
+    def __init__(self, device, maxiter: int, dp: int):
+        self.ws = torch.zeros(int(load().sa_cg_workspace_bytes()) // 4, dtype=torch.float32, device=device)
+        self.stop = torch.zeros(1, dtype=torch.int32, device=device)
+        self.hist = torch.zeros(max(1, maxiter), dp, dtype=torch.float32, device=device)
+        self._pinned = torch.zeros(max(1, maxiter), dtype=torch.int32).pin_memory()
+        self._events = {}
+
+    def poll(self, slot: int):
+        """Enqueue an asynchronous copy of the stop flag as it stands after the work enqueued so far."""
+        self._pinned[slot : slot + 1].copy_(self.stop, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.stop.device))
+        self._events[slot] = ev
+
+    def stopped_at(self, slot: int) -> bool:
+        """Value of the flag at poll `slot` (waits for that copy only; the same on every rank)."""
+        ev = self._events.get(slot)
+        if ev is None:
+            return False
+        ev.synchronize()
+        return bool(self._pinned[slot].item())
+
+    def history(self) -> torch.Tensor:
+        return self.hist.detach().cpu()
+
+
+def _hist_row(cgs: CgScratch, row):
+    return None if row is None else cgs.hist.data_ptr() + row * cgs.hist.stride(0) * 4
+
+
+def coldot(P: torch.Tensor, Q: torch.Tensor, out: torch.Tensor, cgs: CgScratch, hist_row=None, tol: float = 0.0):
+    """out[c] = sum_i P[i,c] Q[i,c]; with `hist_row` the sums are also the residual of that iteration."""
     _req(P, torch.float32, "P")
     _req(Q, torch.float32, "Q")
-    _check(load().sa_coldot(_stream(), P.data_ptr(), Q.data_ptr(), P.shape[0], P.shape[1], out.data_ptr()))
+    track = hist_row is not None
+    _call(load().sa_coldot, P.device, P.data_ptr(), Q.data_ptr(), P.shape[0], P.shape[1], out.data_ptr(),
+          cgs.ws.data_ptr(), _hist_row(cgs, hist_row), cgs.stop.data_ptr() if track else None, float(tol))
     STATS.launches += 1
     return out
 
 
-def cg_update(P, AP, X, R, rs_old, pAp, eps: float, rs_new):
+def cg_update(P, AP, X, R, rs_old, pAp, eps: float, rs_new, cgs: CgScratch, hist_row=None, tol: float = 0.0):
     _req(P, torch.float32, "P")
-    _check(load().sa_cg_update(_stream(), P.shape[0], P.shape[1], P.data_ptr(), _ptr(AP), X.data_ptr(),
-                               _ptr(R), rs_old.data_ptr(), pAp.data_ptr(), float(eps), _ptr(rs_new)))
+    _call(load().sa_cg_update, P.device, P.shape[0], P.shape[1], P.data_ptr(), _ptr(AP), X.data_ptr(),
+          _ptr(R), rs_old.data_ptr(), pAp.data_ptr(), float(eps), _ptr(rs_new), cgs.ws.data_ptr(),
+          _hist_row(cgs, hist_row), cgs.stop.data_ptr(), float(tol))
     STATS.launches += 1
 
 
-def cg_direction(R, P, rs_new, rs_old):
-    _check(load().sa_cg_direction(_stream(), P.shape[0], P.shape[1], R.data_ptr(), P.data_ptr(),
-                                  rs_new.data_ptr(), rs_old.data_ptr()))
+def cg_direction(R, P, rs_new, rs_old, eps: float, cgs: CgScratch):
+    _call(load().sa_cg_direction, P.device, P.shape[0], P.shape[1], R.data_ptr(), P.data_ptr(),
+          rs_new.data_ptr(), rs_old.data_ptr(), float(eps), cgs.stop.data_ptr())
     STATS.launches += 1
 
 
@@ -410,7 +484,7 @@ def axpby(a: float, X: torch.Tensor, b: float, Y: torch.Tensor):
     _req(Y, torch.float32, "Y")
     if X.numel() != Y.numel():
         raise ValueError("size mismatch")
-    _check(load().sa_axpby(_stream(), X.numel(), float(a), X.data_ptr(), float(b), Y.data_ptr()))
+    _call(load().sa_axpby, X.device, X.numel(), float(a), X.data_ptr(), float(b), Y.data_ptr())
     STATS.launches += 1
     return Y
 

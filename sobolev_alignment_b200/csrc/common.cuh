@@ -9,6 +9,11 @@ namespace sab {
 
 void set_error(const char* fmt, ...);  // thread-local message behind sa_last_error()
 
+// Tuning / diagnostic options: sa_set_option() value, else the SAB_* environment
+// variable read once at first use.
+bool option(const char* name, char (&out)[64]);
+int option_int(const char* name, int dflt);
+
 #define SAB_CHECK_CUDA(expr)                                                                 \
   do {                                                                                       \
     cudaError_t _e = (expr);                                                                 \

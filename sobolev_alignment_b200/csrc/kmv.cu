@@ -743,10 +743,7 @@ static int device_info(DeviceInfo* out) {
   return 0;
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* v = std::getenv(name);
-  return v ? std::atoi(v) : dflt;
-}
+static int env_int(const char* name, int dflt) { return option_int(name, dflt); }
 
 // Work decomposition of the fused product.  cbs = number of column chunks that are swept concurrently,
 // the smallest that keeps the A strips of the concurrently running row-tile groups inside an L2 budget;
@@ -922,13 +919,14 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   P.lower = lower;
   P.debug = env_int("SAB_DEBUG", 0);
   {
-    const char* tp = std::getenv("SAB_TRACE_PTR");
-    P.trace = tp ? reinterpret_cast<long long*>(std::strtoull(tp, nullptr, 0)) : nullptr;
+    char tp[64];
+    P.trace = option("SAB_TRACE_PTR", tp) ? reinterpret_cast<long long*>(std::strtoull(tp, nullptr, 0)) : nullptr;
   }
   {
     const float steps = static_cast<float>(P.kblocks * (BK / UMMA_K));
-    const char* sv = std::getenv("SAB_SNAP");  // < 0 disables both corrections (calibration runs)
-    const float forced = sv ? static_cast<float>(std::atof(sv)) : 0.f;
+    char snap_buf[64];
+    const bool sv = option("SAB_SNAP", snap_buf);  // < 0 disables both corrections (calibration runs)
+    const float forced = sv ? static_cast<float>(std::atof(snap_buf)) : 0.f;
     P.snap = sv ? forced : SNAP_PER_STEP * steps + SNAP_FLOOR;
     P.m2g = (sv && forced < 0.f) ? -2.f : -2.f * (1.f + ACC_BIAS_PER_STEP * steps);
   }

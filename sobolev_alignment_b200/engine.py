@@ -159,13 +159,16 @@ class CudaOps:
     potrf = staticmethod(nat.potrf)
     ltl = staticmethod(nat.ltl)
     add_diag = staticmethod(nat.add_diag)
+    trsm_pack = staticmethod(nat.trsm_pack)
     trsm = staticmethod(nat.trsm)
     trsm_pair = staticmethod(nat.trsm_pair)
-    trsm_premul = staticmethod(nat.trsm_premul)
     coldot = staticmethod(nat.coldot)
     cg_update = staticmethod(nat.cg_update)
     cg_direction = staticmethod(nat.cg_direction)
     axpby = staticmethod(nat.axpby)
+
+    def cg_scratch(self, maxiter: int, dp: int):
+        return nat.CgScratch(self.device, maxiter, dp)
 
     def synchronize(self):
         torch.cuda.synchronize(self.device)

@@ -58,41 +58,60 @@ class Comm:
 
 
 class Preconditioner:
-    """Lower Cholesky factors L (= T^T) and LA (= A^T) with their inverted diagonal blocks."""
+    """
+    Lower Cholesky factors L (= T^T) and LA (= A^T) of the Nystrom preconditioner, kept in the packed
+    fp16 hi/lo tile form the triangular solves stream (`ops.trsm_pack`); the fp32 squares are released
+    as soon as they are packed (the packed pair is half their size).
+    """
 
-    def __init__(self, ops, spec: KernelSpec, frame, Cprep, penalty: float, pc_eps: float, comm=None):
+    def __init__(self, ops, spec: KernelSpec, frame, Cprep, penalty: float, pc_eps: float, comm=None,
+                 K: torch.Tensor | None = None):
         M = Cprep.n
         Mp = (M + TILE - 1) // TILE * TILE
         self.ops, self.M, self.Mp = ops, M, Mp
         nblk = Mp // TILE
-        # K_MM, padded with an identity block (leaves factors and solves of the leading block unchanged)
-        K = ops.zeros(Mp, Mp)
-        ops.kdense(spec, frame, Cprep, Cprep, K, symmetric=True)
-        if Mp > M:
-            K.diagonal()[M:] = 1.0
+        distributed = comm is not None and comm.enabled and comm.world > 1
+        if K is None:
+            # K_MM, padded with an identity block (leaves factors and solves of the leading block unchanged)
+            K = ops.zeros(Mp, Mp)
+            ops.kdense(spec, frame, Cprep, Cprep, K, symmetric=True)
+            if Mp > M:
+                K.diagonal()[M:] = 1.0
         ops.add_diag(K, M, pc_eps * M)
-        self.L = K
-        self.L_inv = ops.empty(nblk, TILE, TILE)
+        L = K
+        L_inv = ops.empty(nblk, TILE, TILE)
         self.info = ops.zeros(2, dtype=torch.int32)
-        ops.potrf(self.L, self.L_inv, self.info[0:1])
+        self._potrf(L, L_inv, self.info[0:1], comm if distributed else None)
+        self.G_ltl = None
+        self._finish(L, L_inv, penalty, comm if distributed else None)
+
+    def _potrf(self, A, inv, info, comm):
+        dist_potrf = getattr(self.ops, "potrf_distributed", None)
+        if comm is not None and dist_potrf is not None:
+            dist_potrf(A, inv, info, comm)
+        else:
+            self.ops.potrf(A, inv, info)
+
+    def _finish(self, L, L_inv, penalty, comm):
+        """From the factor L of K_MM + eps M I: G = L^T L / M + lambda I, its factor, and the packed forms."""
+        ops, M, Mp = self.ops, self.M, self.Mp
+        nblk = Mp // TILE
         # A A^T ... : G = L^T L / M + lambda I  (= T T^T / M + lambda I), then its Cholesky factor
-        if comm is not None and comm.enabled and comm.world > 1 and getattr(ops, "ltl_sharded", False):
+        if comm is not None and getattr(ops, "ltl_sharded", False):
             # L^T L has no sequential chain: every rank forms its share of the 512-row slabs and the
             # parts are summed over NVLink (the all-reduce result is identical on all ranks)
             G = ops.zeros(Mp, Mp)
-            ops.ltl(self.L, G, 1.0 / M, 0.0, comm.rank, comm.world)
+            ops.ltl(L, G, 1.0 / M, 0.0, comm.rank, comm.world)
             comm.all_reduce(G)
             ops.add_diag(G, Mp, penalty)
         else:
             G = ops.empty(Mp, Mp)
-            ops.ltl(self.L, G, 1.0 / M, penalty)
-        self.LA = G
-        self.LA_inv = ops.empty(nblk, TILE, TILE)
-        ops.potrf(self.LA, self.LA_inv, self.info[1:2])
-        # pre-multiplied sub-diagonal tiles: one tile product per chain step instead of two
-        premul = getattr(ops, "trsm_premul", None)
-        self.L_w = premul(self.L, self.L_inv) if premul is not None else None
-        self.LA_w = premul(self.LA, self.LA_inv) if premul is not None else None
+            ops.ltl(L, G, 1.0 / M, penalty)
+        self.Lp = ops.trsm_pack(L, L_inv)
+        del L, L_inv
+        LA_inv = ops.empty(nblk, TILE, TILE)
+        self._potrf(G, LA_inv, self.info[1:2], comm)
+        self.LAp = ops.trsm_pack(G, LA_inv)
 
     def check(self):
         info = self.ops.to_host(self.info).tolist()
@@ -104,37 +123,25 @@ class Preconditioner:
 
     # in-place solves on [Mp x dp] buffers
     def invT(self, v):
-        return self.ops.trsm(self.L, self.L_inv, v, True)
+        return self.ops.trsm(self.Lp, v, True)
 
     def invTt(self, v):
-        return self.ops.trsm(self.L, self.L_inv, v, False)
+        return self.ops.trsm(self.Lp, v, False)
 
     def invA(self, v):
-        return self.ops.trsm(self.LA, self.LA_inv, v, True)
+        return self.ops.trsm(self.LAp, v, True)
 
     def invAt(self, v):
-        return self.ops.trsm(self.LA, self.LA_inv, v, False)
+        return self.ops.trsm(self.LAp, v, False)
 
-    # the operator always applies the factors in pairs; one pipelined launch when the engine has it
+    # the operator always applies the factors in pairs: one launch with two interleaved chains
     def invA_invT(self, v, z):
         """v <- A^-1 v (in place);  z <- T^-1 v."""
-        pair = getattr(self.ops, "trsm_pair", None)
-        if pair is not None:
-            return pair(self.LA, self.LA_inv, self.L, self.L_inv, v, z, None, 0.0, True, self.LA_w, self.L_w)
-        self.invA(v)
-        z.copy_(v)
-        return self.invT(z)
+        return self.ops.trsm_pair(self.LAp, self.Lp, v, z, None, 0.0, True)
 
     def invTt_invAt(self, w, out, v=None, lam=0.0):
         """w <- T^-T w (in place);  out <- A^-T (w + lam v)."""
-        pair = getattr(self.ops, "trsm_pair", None)
-        if pair is not None:
-            return pair(self.L, self.L_inv, self.LA, self.LA_inv, w, out, v, lam, False, self.L_w, self.LA_w)
-        self.invTt(w)
-        out.copy_(w)
-        if v is not None:
-            self.ops.axpby(lam, v, 1.0, out)
-        return self.invAt(out)
+        return self.ops.trsm_pair(self.Lp, self.LAp, w, out, v, lam, False)
 
 
 class FalkonSolver:
@@ -292,34 +299,49 @@ class FalkonSolver:
         return alpha
 
     def _conjugate_gradient(self, B, Mp, dp):
+        """
+        Batched-column CG (falkon `ConjugateGradient.solve`).  Convergence is decided by the kernels (a
+        device flag freezes X once max_c sqrt(r_c^T r_c) < cg_tol); the host reads that flag LAG
+        iterations late, so no iteration ends in a device synchronisation, and -- the flag being a
+        function of bit-identical replicated state -- every rank leaves the loop at the same iteration.
+        """
         ops = self.ops
+        LAG = 2
         X = ops.zeros(Mp, dp)
         R = B.clone()
         P = B.clone()
         AP = ops.zeros(Mp, dp)
         rs_old, rs_new, pAp = ops.empty(dp), ops.empty(dp), ops.empty(dp)
-        ops.coldot(R, R, rs_old)
-        self.residuals = []
+        cgs = ops.cg_scratch(self.maxiter, dp)
+        ops.coldot(R, R, rs_old, cgs)
+        done = 0
         for it in range(self.maxiter):
+            if it >= LAG and cgs.stopped_at(it - LAG):
+                break
             self._bhb(P, AP)
-            ops.coldot(P, AP, pAp)
+            ops.coldot(P, AP, pAp, cgs)
             # Falkon recomputes the residual from scratch every `full_grad_every` iterations.  On the very
             # last iteration that product pair would only feed the reported residual (X is final), so
             # the recurrence is used there instead: same alpha, two fused-kernel launches fewer.
             if (it + 1) % self.full_grad_every == 0 and it + 1 < self.maxiter:
-                ops.cg_update(P, None, X, None, rs_old, pAp, self.cg_eps, None)   # X += alpha P
-                self._bhb(X, R)                                                  # R = B - BHB X
+                ops.cg_update(P, None, X, None, rs_old, pAp, self.cg_eps, None, cgs)   # X += alpha P
+                self._bhb(X, R)                                                       # R = B - BHB X
                 ops.axpby(1.0, B, -1.0, R)
-                ops.coldot(R, R, rs_new)
+                ops.coldot(R, R, rs_new, cgs, hist_row=it, tol=self.cg_tol)
             else:
-                ops.cg_update(P, AP, X, R, rs_old, pAp, self.cg_eps, rs_new)
-            self.n_iter_ = it + 1
-            res = float(rs_new.max().sqrt())  # one small D2H read per iteration, as Falkon does
-            self.residuals.append(res)
-            if res < self.cg_tol:
-                break
-            ops.cg_direction(R, P, rs_new, rs_old)
+                ops.cg_update(P, AP, X, R, rs_old, pAp, self.cg_eps, rs_new, cgs, hist_row=it, tol=self.cg_tol)
+            cgs.poll(it)
+            done = it + 1
+            ops.cg_direction(R, P, rs_new, rs_old, self.cg_eps, cgs)
             rs_old, rs_new = rs_new, rs_old
+        # one read of the residual history; iterations after the first converged one were no-ops
+        hist = cgs.history()[:done].double().clamp_min(0).max(dim=1).values.sqrt().tolist()
+        self.residuals = []
+        for r in hist:
+            self.residuals.append(r)
+            if r < self.cg_tol:
+                break
+        self.n_iter_ = len(self.residuals)
         return X
 
     # ------------------------------------------------------------------ release

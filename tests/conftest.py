@@ -36,6 +36,39 @@ def relerr(x, ref):
     return float((x - ref).abs().max() / (den if den > 0 else 1.0))
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need CUDA and the built library: skip them (instead of erroring) where either is missing."""
+    from sobolev_alignment_b200 import _native as nat
+
+    reason = None
+    if not torch.cuda.is_available():
+        reason = "no CUDA device"
+    elif not os.path.exists(nat.library_path()):
+        reason = "libsobolev_b200.so not built"
+    if reason is None:
+        return
+    skip = pytest.mark.skip(reason=reason)
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture
+def sab_option():
+    """Set library options (SAB_*) for one test; restored to the environment's values afterwards."""
+    from sobolev_alignment_b200 import _native as nat
+
+    touched = []
+
+    def _set(name, value):
+        touched.append(name)
+        nat.set_option(name, value)
+
+    yield _set
+    for name in touched:
+        nat.set_option(name, None)
+
+
 @pytest.fixture(scope="session")
 def cuda_ops():
     from sobolev_alignment_b200.engine import CudaOps

@@ -20,6 +20,29 @@ class _Rows:
         self.data, self.n, self.p = data, data.shape[0], data.shape[1]
 
 
+class _CgScratch:
+    """Same contract as _native.CgScratch: residual history, stop flag, late polls."""
+
+    def __init__(self, maxiter, dp):
+        self.hist = torch.zeros(max(1, maxiter), dp, dtype=torch.float64)
+        self.stop = False
+        self._polls = {}
+
+    def record(self, row, sums, tol):
+        self.hist[row] = sums
+        if float(sums.max().clamp_min(0).sqrt()) < tol:
+            self.stop = True
+
+    def poll(self, slot):
+        self._polls[slot] = self.stop
+
+    def stopped_at(self, slot):
+        return self._polls.get(slot, False)
+
+    def history(self):
+        return self.hist
+
+
 class CpuOps:
     name = "cpu-oracle"
 
@@ -67,35 +90,44 @@ class CpuOps:
     def add_diag(self, A, m, value):
         A.diagonal()[:m] += value
 
-    def trsm(self, L, invdiag, B, transpose):
-        Lt = torch.tril(L)
-        B.copy_(torch.linalg.solve_triangular(Lt.T if transpose else Lt, B, upper=bool(transpose)))
+    def trsm_pack(self, L, invdiag):
+        return torch.tril(L).clone()      # the CUDA engine returns the packed fp16 hi/lo tiles
+
+    def trsm(self, F, B, transpose):
+        B.copy_(torch.linalg.solve_triangular(F.T if transpose else F, B, upper=bool(transpose)))
         return B
 
-    def trsm_premul(self, L, invdiag):
-        return "premul-token"          # the CUDA engine returns the pre-multiplied tiles; the stand-in needs none
-
-    def trsm_pair(self, La, inva, Lb, invb, Xa, Xb, V, lam, transpose, Wa=None, Wb=None):
+    def trsm_pair(self, Fa, Fb, Xa, Xb, V, lam, transpose):
         """Xa <- op(La)^-1 Xa ; Xb <- op(Lb)^-1 (Xa + lam V)  (same contract as _native.trsm_pair)."""
-        assert (Wa is None) == (Wb is None)
-        self.trsm(La, inva, Xa, transpose)
+        self.trsm(Fa, Xa, transpose)
         Xb.copy_(Xa if V is None else Xa + lam * V)
-        self.trsm(Lb, invb, Xb, transpose)
+        self.trsm(Fb, Xb, transpose)
         return Xb
 
-    def coldot(self, P, Q, out):
+    def cg_scratch(self, maxiter, dp):
+        return _CgScratch(maxiter, dp)
+
+    def coldot(self, P, Q, out, cgs, hist_row=None, tol=0.0):
         out.copy_((P * Q).sum(0))
+        if hist_row is not None:
+            cgs.record(hist_row, out, tol)
         return out
 
-    def cg_update(self, P, AP, X, R, rs_old, pAp, eps, rs_new):
+    def cg_update(self, P, AP, X, R, rs_old, pAp, eps, rs_new, cgs, hist_row=None, tol=0.0):
+        if cgs.stop:
+            return
         alpha = rs_old / (pAp + eps)
         X += P * alpha[None, :]
         if AP is not None:
             R -= AP * alpha[None, :]
             rs_new.copy_((R * R).sum(0))
+            if hist_row is not None:
+                cgs.record(hist_row, rs_new, tol)
 
-    def cg_direction(self, R, P, rs_new, rs_old):
-        beta = torch.where(rs_old > 0, rs_new / rs_old, torch.zeros_like(rs_old))
+    def cg_direction(self, R, P, rs_new, rs_old, eps, cgs):
+        if cgs.stop:
+            return
+        beta = torch.where(rs_old > 0, rs_new / (rs_old + eps), torch.zeros_like(rs_old))
         P.copy_(R + P * beta[None, :])
 
     def axpby(self, a, X, b, Y):

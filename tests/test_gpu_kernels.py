@@ -344,14 +344,14 @@ def test_kernel_object_is_callable_like_falkon(cuda_ops):
 
 # ---------------------------------------------------------------------------- preconditioner algebra
 @pytest.mark.parametrize("M,dp,nb", [(128, 4, None), (384, 12, 128), (1024, 20, None), (2048, 32, 256), (2048, 20, "simt")])
-def test_cholesky_ltl_trsm(cuda_ops, M, dp, nb, monkeypatch):
+def test_cholesky_ltl_trsm(cuda_ops, M, dp, nb, sab_option):
     """potrf / ltl on the tensor-core path (several outer panel widths) and on the fp32 SIMT path."""
     from sobolev_alignment_b200 import _native as nat
 
     if nb == "simt":
-        monkeypatch.setenv("SAB_LINALG_SIMT", "1")
+        sab_option("SAB_LINALG_SIMT", "1")
     elif nb is not None:
-        monkeypatch.setenv("SAB_CHOL_NB", str(nb))
+        sab_option("SAB_CHOL_NB", str(nb))
 
     g = torch.Generator().manual_seed(M)
     Z = torch.randn(M, 24, generator=g, dtype=torch.float64)
@@ -368,17 +368,26 @@ def test_cholesky_ltl_trsm(cuda_ops, M, dp, nb, monkeypatch):
     Gref = Lref.T @ Lref / M + 1e-3 * torch.eye(M, dtype=torch.float64)
     assert relerr(torch.tril(G), torch.tril(Gref)) < FP32_TOL
     B = torch.randn(M, dp, generator=g)
+    F = nat.trsm_pack(A, inv)
     for tr in (False, True):
         X = B.cuda()
-        nat.trsm(A, inv, X, tr)
+        nat.trsm(F, X, tr)
         ref = torch.linalg.solve_triangular(Lref.T if tr else Lref, B.double(), upper=tr)
         assert relerr(X, ref) < 5e-5
 
 
-@pytest.mark.parametrize("M,dp", [(128, 4), (1024, 20), (4096, 12)])
-def test_paired_solves_match_two_single_solves(cuda_ops, M, dp, monkeypatch):
-    """sa_trsm_pair (two pipelined chains in one launch) against two sa_trsm calls, both directions, with the lambda V term."""
+@pytest.mark.parametrize("M,dp,chunk", [(128, 4, None), (1024, 20, None), (4096, 12, None), (4096, 28, "4"),
+                                        (2304, 8, "2")])
+def test_paired_solves_match_two_single_solves(cuda_ops, M, dp, chunk, sab_option):
+    """
+    sa_trsm_solve_pair (two interleaved chains in one launch) against two sa_trsm_solve calls and against
+    float64, both directions, with the lambda V term; several chunk lengths of the work decomposition
+    (option SAB_TRSM_CHUNK; the default is 16 tiles per item).
+    """
     from sobolev_alignment_b200 import _native as nat
+
+    if chunk:
+        sab_option("SAB_TRSM_CHUNK", chunk)
 
     g = torch.Generator(device="cuda").manual_seed(M)
     facs = []
@@ -390,35 +399,34 @@ def test_paired_solves_match_two_single_solves(cuda_ops, M, dp, monkeypatch):
         info = torch.zeros(1, dtype=torch.int32, device="cuda")
         nat.potrf(A, inv, info)
         assert int(info) == 0
-        facs.append((A, inv))
-    (La, ia), (Lb, ib) = facs
+        facs.append((nat.trsm_pack(A, inv), torch.tril(A).double()))
+    (Fa, La), (Fb, Lb) = facs
     B = torch.randn(M, dp, device="cuda", generator=g)
     V = torch.randn(M, dp, device="cuda", generator=g)
     for tr in (False, True):
         for lam, Vt in ((0.0, None), (0.37, V)):
             xa = B.clone()
-            nat.trsm(La, ia, xa, tr)
+            nat.trsm(Fa, xa, tr)
             xb = xa.clone() if Vt is None else (xa + lam * Vt)
-            nat.trsm(Lb, ib, xb, tr)
+            nat.trsm(Fb, xb, tr)
+            ra = torch.linalg.solve_triangular(La.T if tr else La, B.double(), upper=tr)
+            rb = torch.linalg.solve_triangular(Lb.T if tr else Lb, ra if Vt is None else ra + lam * Vt.double(),
+                                               upper=tr)
+            assert relerr(xa, ra) < 2e-5 and relerr(xb, rb) < 2e-5
             pa, pb = B.clone(), torch.full_like(B, float("nan"))
-            nat.trsm_pair(La, ia, Lb, ib, pa, pb, Vt, lam, tr)
-            assert torch.equal(pa, xa)                 # same arithmetic, same order: bit identical
-            assert relerr(pb, xb.double()) < FP32_TOL
-            # with the pre-multiplied sub-diagonal tiles (x_c = inv (b - S) - W x_{c-1}: another rounding order)
-            wa, wb = nat.trsm_premul(La, ia), nat.trsm_premul(Lb, ib)
-            for f16 in ("0", "1"):                      # 3xTF32 (default) and fp16 hi/lo tile products
-                monkeypatch.setenv("SAB_TRSM_F16", f16)
-                qa, qb = B.clone(), torch.full_like(B, float("nan"))
-                nat.trsm_pair(La, ia, Lb, ib, qa, qb, Vt, lam, tr, wa, wb)
-                assert relerr(qa, xa.double()) < FP32_TOL and relerr(qb, xb.double()) < FP32_TOL
-            monkeypatch.delenv("SAB_TRSM_F16")
+            nat.trsm_pair(Fa, Fb, pa, pb, Vt, lam, tr)
+            assert torch.equal(pa, xa) and torch.equal(pb, xb)   # fixed summation order: bit identical
+            # and reproducible run to run (no atomics, no order dependence on the CTA schedule)
+            qa, qb = B.clone(), torch.full_like(B, float("nan"))
+            nat.trsm_pair(Fa, Fb, qa, qb, Vt, lam, tr)
+            assert torch.equal(qa, pa) and torch.equal(qb, pb)
 
 
-def test_ltl_parts_sum_to_the_whole(cuda_ops, monkeypatch):
+def test_ltl_parts_sum_to_the_whole(cuda_ops, sab_option):
     """sa_ltl_part: the shares of 3 'ranks' (slabs dealt out cyclically) add up to sa_ltl's G."""
     from sobolev_alignment_b200 import _native as nat
 
-    monkeypatch.setenv("SAB_CHOL_NB", "256")      # 8 slabs at M = 2048
+    sab_option("SAB_CHOL_NB", "256")      # 8 slabs at M = 2048
     M = 2048
     g = torch.Generator(device="cuda").manual_seed(2)
     Z = torch.randn(M, 24, device="cuda", generator=g)
@@ -462,10 +470,10 @@ def test_large_factorisation_and_chained_solves(cuda_ops):
     assert float(R.abs().max()) < 2e-5
     del R
     B = torch.randn(M, dp, device="cuda", generator=g)
-    Lf = L.float().contiguous()
+    F = nat.trsm_pack(L.float().contiguous(), inv)
     for tr in (False, True):
         X = B.clone()
-        nat.trsm(Lf, inv, X, tr)
+        nat.trsm(F, X, tr)
         ref = torch.linalg.solve_triangular(L.T if tr else L, B.double(), upper=tr)
         assert relerr(X, ref) < 2e-4, (tr, relerr(X, ref))
 
@@ -483,25 +491,39 @@ def test_cholesky_flags_non_positive_definite(cuda_ops):
 def test_cg_vector_kernels(cuda_ops):
     from sobolev_alignment_b200 import _native as nat
 
-    M, dp = 5000, 20
+    M, dp = 50000, 20        # several blocks per column reduction
     g = torch.Generator().manual_seed(0)
     P, Q, X, R = (torch.randn(M, dp, generator=g) for _ in range(4))
     rs_old, pAp = torch.rand(dp, generator=g) + 0.5, torch.rand(dp, generator=g) + 0.5
+    cgs = nat.CgScratch(torch.device("cuda", torch.cuda.current_device()), 4, dp)
     out = torch.empty(dp, device="cuda")
-    nat.coldot(P.cuda(), Q.cuda(), out)
+    nat.coldot(P.cuda(), Q.cuda(), out, cgs)
     assert relerr(out, (P.double() * Q.double()).sum(0)) < 1e-5
+    out2 = torch.empty(dp, device="cuda")
+    nat.coldot(P.cuda(), Q.cuda(), out2, cgs)
+    assert torch.equal(out, out2)                      # deterministic reduction (no float atomics)
     Xd, Rd, rs_new = X.cuda(), R.cuda(), torch.empty(dp, device="cuda")
-    nat.cg_update(P.cuda(), Q.cuda(), Xd, Rd, rs_old.cuda(), pAp.cuda(), 1e-7, rs_new)
+    nat.cg_update(P.cuda(), Q.cuda(), Xd, Rd, rs_old.cuda(), pAp.cuda(), 1e-7, rs_new, cgs, hist_row=1, tol=1e-7)
     al = (rs_old / (pAp + 1e-7)).double()
     assert relerr(Xd, X.double() + P.double() * al) < 1e-6
     assert relerr(Rd, R.double() - Q.double() * al) < 1e-6
     assert relerr(rs_new, ((R.double() - Q.double() * al) ** 2).sum(0)) < 1e-5
+    assert torch.equal(cgs.history()[1], rs_new.cpu()) and int(cgs.stop) == 0
     Pd = P.cuda()
     rs_old0 = rs_old.clone()
     rs_old0[3] = 0.0                                   # an exactly converged / padded column
-    nat.cg_direction(Rd, Pd, rs_new, rs_old0.cuda())
-    beta = torch.where(rs_old0 > 0, rs_new.cpu() / rs_old0, torch.zeros(dp)).double()
+    nat.cg_direction(Rd, Pd, rs_new, rs_old0.cuda(), 1e-7, cgs)
+    beta = torch.where(rs_old0 > 0, rs_new.cpu() / (rs_old0 + 1e-7), torch.zeros(dp)).double()
     assert relerr(Pd, Rd.cpu().double() + P.double() * beta) < 1e-6
     Y = Q.cuda()
     nat.axpby(0.5, P.cuda(), 2.0, Y)
     assert relerr(Y, 0.5 * P.double() + 2 * Q.double()) < 1e-6
+    # convergence: a tiny residual raises the device flag, after which update / direction are frozen
+    tiny = torch.full((M, dp), 1e-12, device="cuda")
+    nat.coldot(tiny, tiny, out, cgs, hist_row=2, tol=1e-7)
+    cgs.poll(2)
+    assert cgs.stopped_at(2) and not cgs.stopped_at(0)
+    Xf, Pf = Xd.clone(), Pd.clone()
+    nat.cg_update(P.cuda(), Q.cuda(), Xd, Rd, rs_old.cuda(), pAp.cuda(), 1e-7, rs_new, cgs, hist_row=3, tol=1e-7)
+    nat.cg_direction(Rd, Pd, rs_new, rs_old.cuda(), 1e-7, cgs)
+    assert torch.equal(Xf, Xd) and torch.equal(Pf, Pd)

@@ -14,7 +14,7 @@ from conftest import krr_test_data, load_golden, relerr
 def test_sklearn_pin_recorded():
     """The generating script asserted <1e-6; the fixture records what it measured (~2e-11)."""
     g = load_golden("sklearn_pin")
-    for name in ("matern15", "rbf"):
+    for name in ("laplacian", "matern15", "matern25", "rbf"):
         assert float(g[f"{name}_err"]) < 1e-9
         assert relerr(g[f"{name}_oracle_pred"], g[f"{name}_ref_pred"]) < 1e-9
 
@@ -25,9 +25,11 @@ def test_oracle_reproduces_sklearn_pin():
     n, p, d = 400, 60, 5
     X, Xv, W, Y, Yv = krr_test_data(seed=11, n=n, p=p, d=d, n_valid=40)
     sigma = float(np.sqrt(2 * p))
-    alpha = fo.falkon_fit(X, Y, X, "matern", sigma, 1e-4, nu=1.5, pc_eps=1e-13, cg_eps=1e-15)
-    pred = fo.falkon_predict(Xv, X, alpha, "matern", sigma, 1.5)
-    assert relerr(pred, g["matern15_ref_pred"]) < 1e-8
+    for name, kern, nu in (("laplacian", "laplacian", None), ("matern15", "matern", 1.5),
+                           ("matern25", "matern", 2.5), ("rbf", "gaussian", None)):
+        alpha = fo.falkon_fit(X, Y, X, kern, sigma, 1e-4, nu=nu, pc_eps=1e-13, cg_eps=1e-15)
+        pred = fo.falkon_predict(Xv, X, alpha, kern, sigma, nu)
+        assert relerr(pred, g[f"{name}_ref_pred"]) < 1e-8, name
 
 
 def test_matern_matches_sklearn_kernel():

@@ -121,27 +121,29 @@ def check_linalg():
         Gref = Lref.T @ Lref / M + 1e-3 * torch.eye(M, device=dev, dtype=torch.float64)
         print(f"ltl M={M}: relerr={relerr(torch.tril(G), torch.tril(Gref)):.2e}")
         B = torch.randn(M, dp, device=dev, generator=g)
+        F = nat.trsm_pack(A, invd)
         for tr in (False, True):
             X = B.clone()
-            nat.trsm(A, invd, X, tr)
+            nat.trsm(F, X, tr)
             torch.cuda.synchronize()
             ref = torch.linalg.solve_triangular(Lref.T if tr else Lref, B.double(), upper=tr)
             print(f"trsm M={M} dp={dp} trans={tr}: relerr={relerr(X, ref):.2e}")
         P = torch.randn(M, dp, device=dev, generator=g); Q = torch.randn(M, dp, device=dev, generator=g)
         out = torch.empty(dp, device=dev)
-        nat.coldot(P, Q, out)
+        cgs = nat.CgScratch(dev if isinstance(dev, torch.device) else torch.device(dev), 2, dp)
+        nat.coldot(P, Q, out, cgs)
         print(f"coldot relerr={relerr(out, (P.double() * Q.double()).sum(0)):.2e}")
         X = torch.randn(M, dp, device=dev, generator=g); R = torch.randn(M, dp, device=dev, generator=g)
         rs_old = torch.rand(dp, device=dev) + 0.5; pAp = torch.rand(dp, device=dev) + 0.5
         rs_new = torch.empty(dp, device=dev)
         X0, R0 = X.clone(), R.clone()
-        nat.cg_update(P, Q, X, R, rs_old, pAp, 1e-7, rs_new)
+        nat.cg_update(P, Q, X, R, rs_old, pAp, 1e-7, rs_new, cgs)
         al = rs_old / (pAp + 1e-7)
         print(f"cg_update X={relerr(X, (X0 + P * al).double()):.2e} R={relerr(R, (R0 - Q * al).double()):.2e} "
               f"rs={relerr(rs_new, ((R0 - Q * al).double() ** 2).sum(0)):.2e}")
         P0 = P.clone()
-        nat.cg_direction(R, P, rs_new, rs_old)
-        print(f"cg_direction={relerr(P, (R + P0 * (rs_new / rs_old)).double()):.2e}")
+        nat.cg_direction(R, P, rs_new, rs_old, 1e-7, cgs)
+        print(f"cg_direction={relerr(P, (R + P0 * (rs_new / (rs_old + 1e-7))).double()):.2e}")
         Y = Q.clone()
         nat.axpby(0.5, P, 2.0, Y)
         print(f"axpby={relerr(Y, (0.5 * P + 2 * Q).double()):.2e}")
@@ -200,18 +202,31 @@ def bench_linalg():
         invd2 = torch.empty(M // 128, 128, 128, device=dev)
         t5 = timed(lambda: nat.potrf(G, invd2, info2))
         B = torch.randn(M, 20, device=dev)
-        t3 = timed(lambda: nat.trsm(A, invd, B, False))
-        t4 = timed(lambda: nat.trsm(A, invd, B, True))
+        B0 = B.clone()
+        holder = {}
+        t6 = timed(lambda: holder.__setitem__("F", nat.trsm_pack(A, invd)))
+        F = holder["F"]
+        F2 = nat.trsm_pack(G, invd2)
+        B2 = torch.empty_like(B)
+        def best(fn, reps=5):
+            fn()
+            return min(timed(fn) for _ in range(reps))
+
+        t3 = best(lambda: nat.trsm(F, B.copy_(B0), False))
+        t4 = best(lambda: nat.trsm(F, B.copy_(B0), True))
+        t7 = best(lambda: nat.trsm_pair(F, F2, B.copy_(B0), B2, None, 0.0, False))
+        t8 = best(lambda: nat.trsm_pair(F, F2, B.copy_(B0), B2, None, 0.0, True))
         print(f"M={M}: potrf {t1*1e3:.1f} ms ({M**3/3/t1/1e12:.1f} TFLOP/s) ltl {t2*1e3:.1f} ms "
-              f"({M**3/3/t2/1e12:.1f} TFLOP/s) potrf(G) {t5*1e3:.1f} ms trsm fwd {t3*1e3:.2f} ms ({M*M*2/t3/1e9:.0f} GB/s) "
-              f"bwd {t4*1e3:.2f} ms info={int(info)},{int(info2)}", flush=True)
-        del A, G, invd, invd2, B
+              f"({M**3/3/t2/1e12:.1f} TFLOP/s) potrf(G) {t5*1e3:.1f} ms pack {t6*1e3:.1f} ms trsm fwd {t3*1e3:.2f} ms "
+              f"({M*M*2/t3/1e9:.0f} GB/s) bwd {t4*1e3:.2f} ms pair fwd {t7*1e3:.2f} ms ({M*M*4/t7/1e9:.0f} GB/s) "
+              f"bwd {t8*1e3:.2f} ms info={int(info)},{int(info2)}", flush=True)
+        del A, G, invd, invd2, B, F, F2
 
 
 def check_accum():
     """How far is |a|^2+|a|^2-2a.a from zero (relative to |a|^2+|a|^2)?  tcgen05 accumulation resolution."""
     import numpy as np
-    os.environ["SAB_SNAP"] = "-1"   # disable the snap: look at the raw computed distances
+    nat.set_option("SAB_SNAP", "-1")   # disable the snap: look at the raw computed distances
     from sobolev_alignment_b200 import synthetic as syn
     for p in (64, 256, 512, 1024, 2048, 3000, 4096):
         for name, A in (("normal", torch.randn(1024, p, device=dev)),

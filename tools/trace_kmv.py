@@ -13,7 +13,7 @@ from sobolev_alignment_b200 import _native as nat  # noqa: E402
 
 dev = torch.device("cuda:0")
 if len(sys.argv) > 1:
-    os.environ["SAB_DEBUG"] = sys.argv[1]
+    nat.set_option("SAB_DEBUG", sys.argv[1])
 a, b, p, d = 148 * 128 * 2, 50000, 3000, 20
 A = torch.randn(a, p, device=dev) * 0.2
 B = torch.randn(b, p, device=dev) * 0.2
@@ -24,7 +24,7 @@ out = torch.zeros(a, d, device=dev)
 nat.kmv(1, 0.1, PA, PB, V, out)
 torch.cuda.synchronize()
 trace = torch.zeros(4000, dtype=torch.int64, device=dev)
-os.environ["SAB_TRACE_PTR"] = str(trace.data_ptr())
+nat.set_option("SAB_TRACE_PTR", str(trace.data_ptr()))
 nat.kmv(1, 0.1, PA, PB, V, out)
 torch.cuda.synchronize()
 ev = trace.cpu().view(-1, 2).tolist()
