@@ -35,6 +35,10 @@ Kernel definitions (what `falkon.kernels.*` compute; restated from the Falkon do
 Everything is computed in float64; distances are formed from explicit differences for small
 problems (no ||x||^2+||y||^2-2xy cancellation), so the oracle does not share the GPU path's
 rounding behaviour.
+
+The functions are device-agnostic torch code: the BASELINE-scale parity tests (tests/test_gpu_scale.py)
+hand them CUDA float64 tensors so the same restatement finishes in seconds (torch / cuBLAS / cuSOLVER
+float64 -- none of this repository's kernels); every fixture and small test runs them on the CPU.
 """
 
 from __future__ import annotations
@@ -79,7 +83,7 @@ def sq_dists(A: torch.Tensor, B: torch.Tensor, direct: bool | None = None) -> to
     if direct is None:
         direct = A.shape[0] * B.shape[0] * A.shape[1] <= 2_000_000_000
     if direct:
-        out = torch.empty(A.shape[0], B.shape[0], dtype=torch.float64)
+        out = torch.empty(A.shape[0], B.shape[0], dtype=torch.float64, device=A.device)
         step = max(1, int(32_000_000 // max(1, B.shape[0] * A.shape[1])))
         for s in range(0, A.shape[0], step):
             diff = A[s : s + step, None, :] - B[None, :, :]
@@ -120,7 +124,7 @@ class Preconditioner:
 
     def __init__(self, K_MM: torch.Tensor, penalty: float, pc_eps: float = PC_EPSILON_F32):
         M = K_MM.shape[0]
-        eye = torch.eye(M, dtype=torch.float64)
+        eye = torch.eye(M, dtype=torch.float64, device=K_MM.device)
         self.T = torch.linalg.cholesky(K_MM.to(torch.float64) + pc_eps * M * eye, upper=True)
         self.A = torch.linalg.cholesky(self.T @ self.T.T / M + penalty * eye, upper=True)
 
@@ -179,7 +183,7 @@ def falkon_fit(X, Y, centres, kernel, sigma, penalty, nu=None, maxiter=20, row_b
 
     def knm_t_knm(u, w=None):
         """sum over row blocks of Kb^T (Kb u + w_b)   (Falkon `dmmv`)."""
-        out = torch.zeros(C.shape[0], Y.shape[1] if u is None else u.shape[1], dtype=torch.float64)
+        out = torch.zeros(C.shape[0], Y.shape[1] if u is None else u.shape[1], dtype=torch.float64, device=X.device)
         for s in range(0, n, row_block):
             Kb = kernel_matrix(X[s : s + row_block], C, kernel, sigma, nu)
             t = Kb @ u if u is not None else 0.0

@@ -78,12 +78,12 @@ class Preconditioner:
             if Mp > M:
                 K.diagonal()[M:] = 1.0
         ops.add_diag(K, M, pc_eps * M)
-        L = K
         L_inv = ops.empty(nblk, TILE, TILE)
         self.info = ops.zeros(2, dtype=torch.int32)
-        self._potrf(L, L_inv, self.info[0:1], comm if distributed else None)
-        self.G_ltl = None
-        self._finish(L, L_inv, penalty, comm if distributed else None)
+        self._potrf(K, L_inv, self.info[0:1], comm if distributed else None)   # in place: K now holds L
+        held = [K, L_inv]
+        del K, L_inv        # `held` is the only reference: _finish releases the fp32 factor once it is packed
+        self._finish(held, penalty, comm if distributed else None)
 
     def _potrf(self, A, inv, info, comm):
         dist_potrf = getattr(self.ops, "potrf_distributed", None)
@@ -92,9 +92,10 @@ class Preconditioner:
         else:
             self.ops.potrf(A, inv, info)
 
-    def _finish(self, L, L_inv, penalty, comm):
+    def _finish(self, held, penalty, comm):
         """From the factor L of K_MM + eps M I: G = L^T L / M + lambda I, its factor, and the packed forms."""
         ops, M, Mp = self.ops, self.M, self.Mp
+        L, L_inv = held
         nblk = Mp // TILE
         # A A^T ... : G = L^T L / M + lambda I  (= T T^T / M + lambda I), then its Cholesky factor
         if comm is not None and getattr(ops, "ltl_sharded", False):
@@ -108,6 +109,7 @@ class Preconditioner:
             G = ops.empty(Mp, Mp)
             ops.ltl(L, G, 1.0 / M, penalty)
         self.Lp = ops.trsm_pack(L, L_inv)
+        held.clear()
         del L, L_inv
         LA_inv = ops.empty(nblk, TILE, TILE)
         self._potrf(G, LA_inv, self.info[1:2], comm)

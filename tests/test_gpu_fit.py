@@ -141,7 +141,7 @@ def test_save_load_roundtrip_and_multi(tmp_path):
     for f in ("params.pkl", "sample_anchors.pt", "sample_weights.pt", "sample_anchors.csv", "sample_weights.csv"):
         assert os.path.exists(os.path.join(folder, f))
     clf2 = KRRApprox.load(folder)
-    assert torch.equal(clf2.transform(Xv), pred)
+    assert relerr(clf2.transform(Xv), pred) < 1e-6      # (kmv sums column chunks with float atomics)
     multi = MultiKRRApprox()
     multi.add_clf(clf)
     multi.add_clf(clf2)
@@ -208,7 +208,9 @@ def _sharded_rank_main(rank, world, port, out_dir):
         X, Xv = torch.from_numpy(Xall[:3001]), torch.from_numpy(Xall[3001:])
         bounds = np.linspace(0, X.shape[0], world + 1).astype(int)
         Xl, Yl = X[bounds[rank]:bounds[rank + 1]], Y[bounds[rank]:bounds[rank + 1]]
-        clf = Falkon(kernel=LaplacianKernel(sigma=9.0), penalty=1e-4, M=400, seed=5,
+        # M = 1500: the CG column reductions span several blocks (deterministic two-pass sums keep the
+        # replicated state bit-identical across ranks -- ADVICE round 1)
+        clf = Falkon(kernel=LaplacianKernel(sigma=9.0), penalty=1e-4, M=1500, seed=5,
                      options=FalkonOptions(row_sharded=True))
         clf.fit(Xl, Yl)
         pred = clf.predict(Xv)
@@ -241,7 +243,7 @@ def test_row_sharded_fit_on_gpu_world2(tmp_path):
     Xall = syn.log_counts_numpy(3001 + 40, 300, seed=4)
     Y = torch.from_numpy(syn.targets_numpy(Xall, 5, seed=6)[:3001])
     X, Xv = torch.from_numpy(Xall[:3001]), torch.from_numpy(Xall[3001:])
-    idx = np.sort(np.random.default_rng(5).choice(3001, size=400, replace=False))
+    idx = np.sort(np.random.default_rng(5).choice(3001, size=1500, replace=False))
     assert torch.equal(r0["centres"], X[idx])
     ref = fo.falkon_fit(X, Y, X[idx], "laplacian", 9.0, 1e-4)
     refp = fo.falkon_predict(Xv, X[idx], ref, "laplacian", 9.0)
