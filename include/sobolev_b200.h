@@ -122,6 +122,29 @@ int64_t sa_linalg_workspace_bytes(int64_t M);
 int sa_potrf(void* stream, float* A, int64_t M, int64_t lda, float* invdiag, int* info, void* workspace,
              int64_t workspace_bytes);
 
+/*
+ * The same factorisation in steps, for the row-sharded (multi-GPU) solver: the outer panels of
+ * sa_potrf_outer_blocks() block columns are dealt out over the ranks, the owner factors a panel, the panel
+ * travels by NCCL broadcast (outside this ABI) and every rank applies it to the panels it owns.
+ *   sa_potrf_begin   once: clears `info`, derives the operand scale of the tensor-core updates
+ *   sa_potrf_panel   factor block columns [k0, kend) (all rows below) in place; their earlier updates
+ *                    must have been applied
+ *   sa_potrf_split   fp16 hi/lo operands of a finished panel; `panel` = its rows BELOW its diagonal
+ *                    blocks, [rows x W] fp32 with row stride ldp (a slice of A, or a received copy)
+ *   sa_potrf_update  C -= P P^T restricted to block columns [c0, c1) (rows from block c0 down) of the
+ *                    trailing matrix that starts at block kend, P = the panel last split
+ * sa_potrf == begin; for each panel: panel, split, update(kend, kend, M/128).
+ */
+int sa_potrf_outer_blocks(void);
+int sa_potrf_begin(void* stream, const float* A, int64_t M, int64_t lda, int* info, void* workspace,
+                   int64_t workspace_bytes);
+int sa_potrf_panel(void* stream, float* A, int64_t M, int64_t lda, float* invdiag, int* info, int k0,
+                   int kend);
+int sa_potrf_split(void* stream, int64_t M, const float* panel, int64_t ldp, int64_t rows, int W,
+                   void* workspace, int64_t workspace_bytes);
+int sa_potrf_update(void* stream, float* A, int64_t M, int64_t lda, int kend, int c0, int c1,
+                    const float* panel, int64_t ldp, int W, void* workspace, int64_t workspace_bytes);
+
 /* G(lower) = alpha * L^T L + beta * I   (falkon `lauum` + `mul_triang` + add-diagonal [ext]);
  * same workspace contract as sa_potrf. */
 int sa_ltl(void* stream, const float* L, int64_t M, int64_t ldl, float* G, int64_t ldg, float alpha,

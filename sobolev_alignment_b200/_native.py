@@ -78,6 +78,12 @@ _SIGNATURES = {
                           c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int]),
     "sa_linalg_workspace_bytes": (c_int64, [c_int64]),
     "sa_potrf": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64]),
+    "sa_potrf_outer_blocks": (c_int, []),
+    "sa_potrf_begin": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64]),
+    "sa_potrf_panel": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int]),
+    "sa_potrf_split": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64]),
+    "sa_potrf_update": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_int,
+                                c_void_p, c_int64]),
     "sa_ltl": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p,
                        c_int64]),
     "sa_ltl_part": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p,
@@ -327,6 +333,43 @@ def potrf(A: torch.Tensor, invdiag: torch.Tensor, info: torch.Tensor):
                            info.data_ptr(), ws.data_ptr(), ws.numel())
     nblk = A.shape[0] // TILE
     STATS.launches += 2 + nblk + 3 * (nblk - 1)   # scale, diagonal blocks, (panel, split, update) per step
+
+
+# ---- the factorisation in steps (row-sharded solver: outer panels dealt out over the ranks)
+def potrf_outer_blocks() -> int:
+    """Width of an outer panel in 128-blocks (0: the fp32 SIMT cross-check path is selected)."""
+    return int(load().sa_potrf_outer_blocks())
+
+
+def potrf_begin(A: torch.Tensor, info: torch.Tensor):
+    _req(A, torch.float32, "A")
+    ws = _linalg_workspace(A.device, A.shape[0])
+    _call(load().sa_potrf_begin, A.device, A.data_ptr(), A.shape[0], A.stride(0), info.data_ptr(), ws.data_ptr(),
+          ws.numel())
+    STATS.launches += 2
+
+
+def potrf_panel(A: torch.Tensor, invdiag: torch.Tensor, info: torch.Tensor, k0: int, kend: int):
+    _call(load().sa_potrf_panel, A.device, A.data_ptr(), A.shape[0], A.stride(0), invdiag.data_ptr(), info.data_ptr(),
+          int(k0), int(kend))
+    STATS.launches += 3 * (kend - k0)
+
+
+def potrf_split(m: int, panel: torch.Tensor, W: int):
+    """`panel`: [rows x W] fp32 view (unit column stride) of the finished panel below its diagonal blocks."""
+    if panel.dtype != torch.float32 or panel.stride(1) != 1 or panel.shape[1] != W:
+        raise ValueError("panel must be a float32 [rows x W] view with unit column stride")
+    ws = _linalg_workspace(panel.device, m)
+    _call(load().sa_potrf_split, panel.device, m, panel.data_ptr(), panel.stride(0), panel.shape[0], int(W),
+          ws.data_ptr(), ws.numel())
+    STATS.launches += 1
+
+
+def potrf_update(A: torch.Tensor, kend: int, c0: int, c1: int, panel: torch.Tensor, W: int):
+    ws = _linalg_workspace(A.device, A.shape[0])
+    _call(load().sa_potrf_update, A.device, A.data_ptr(), A.shape[0], A.stride(0), int(kend), int(c0), int(c1),
+          panel.data_ptr(), panel.stride(0), int(W), ws.data_ptr(), ws.numel())
+    STATS.launches += 3
 
 
 def ltl(L: torch.Tensor, G: torch.Tensor, alpha: float, beta: float, part: int = 0, nparts: int = 1):

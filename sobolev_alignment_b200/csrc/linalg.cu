@@ -550,19 +550,13 @@ static LinalgWs carve(void* workspace, int64_t M) {
   return w;
 }
 
-extern "C" int sa_potrf(void* stream, float* A, int64_t M, int64_t lda, float* invdiag, int* info,
-                        void* workspace, int64_t workspace_bytes) {
-  SAB_REQUIRE_MAT(M, lda, A);
-  SAB_REQUIRE(invdiag != nullptr && info != nullptr, "invdiag / info must not be NULL");
-  SAB_REQUIRE_WS(M, workspace, workspace_bytes);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int nblk = static_cast<int>(M / TS);
-  const int dsmem = (TS * LDD + 4 * TS) * static_cast<int>(sizeof(float));
-  SAB_CHECK_CUDA(cudaFuncSetAttribute(diag_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dsmem));
+// ---- building blocks of the two-level Cholesky.  sa_potrf strings them together on one GPU; the
+// row-sharded solver (sobolev_alignment_b200/distributed.py) deals the outer panels out over the ranks:
+// the owner factors a panel (sa_potrf_panel), the panel travels by NCCL broadcast, every rank applies it to
+// the outer panels it owns (sa_potrf_split once, sa_potrf_update per owned panel).
+static int potrf_begin(cudaStream_t st, const float* A, int64_t M, int64_t lda, int* info, const LinalgWs& w,
+                       bool tensor) {
   SAB_CHECK_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
-  const bool tensor = use_tensor_path();
-  const int nbb = tensor ? outer_blocks() : nblk;  // SIMT: classic right-looking (one "outer panel")
-  const LinalgWs w = carve(workspace, M);
   if (tensor) {
     // |L_ij| <= sqrt(max_i A_ii): one power-of-two operand scale for the whole factorisation
     SAB_CHECK_CUDA(cudaMemsetAsync(w.hdr, 0, HDR_FLOATS * 4, st));
@@ -570,41 +564,130 @@ extern "C" int sa_potrf(void* stream, float* A, int64_t M, int64_t lda, float* i
                                                                       reinterpret_cast<unsigned*>(w.hdr));
     make_scale_kernel<<<1, 1, 0, st>>>(w.hdr, 1);
   }
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// factor the outer panel: block columns [k0, kend) x all rows below, 128-wide fp32 SIMT steps.
+// inner_limit = last block column (exclusive) the in-panel updates reach: kend on the tensor path (the
+// rest is the trailing update), nblk on the SIMT path (classic right-looking).
+static int potrf_panel(cudaStream_t st, float* A, int64_t lda, float* invdiag, int* info, int nblk, int k0,
+                       int kend, int inner_limit) {
+  const int dsmem = (TS * LDD + 4 * TS) * static_cast<int>(sizeof(float));
+  SAB_CHECK_CUDA(cudaFuncSetAttribute(diag_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dsmem));
+  for (int k = k0; k < kend; ++k) {
+    diag_factor_kernel<<<1, 256, dsmem, st>>>(A, lda, k, invdiag, info);
+    const int rem = nblk - k - 1;
+    if (rem == 0) break;
+    sgemm_kernel<MODE_PANEL><<<rem, 256, 0, st>>>(A, lda, invdiag + static_cast<long long>(k) * TS * TS, TS, k,
+                                                  nblk, 0.f, 0.f);
+    const int jlim = inner_limit - k - 1;  // block columns right of k still inside the panel
+    if (jlim >= rem)
+      sgemm_kernel<MODE_SYRK><<<rem * (rem + 1) / 2, 256, 0, st>>>(A, lda, nullptr, 0, k, nblk,
+                                                                   static_cast<float>(jlim), 0.f);
+    else if (jlim > 0)
+      sgemm_kernel<MODE_SYRK><<<rem * jlim, 256, 0, st>>>(A, lda, nullptr, 0, k, nblk, static_cast<float>(jlim), 0.f);
+  }
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// fp16 hi/lo operands of a finished panel: `panel` = its rows BELOW the panel's diagonal blocks
+// ([rows x W] fp32, row stride ldp), for the tensor-core trailing update
+static int potrf_split(cudaStream_t st, const float* panel, int64_t ldp, long long rows, int W, const LinalgWs& w) {
+  split_f16_kernel<<<static_cast<int>(ceil_div(rows * (W / 8), 256)), 256, 0, st>>>(panel, ldp, rows, W, 0, 0, w.hdr,
+                                                                                 w.opA, w.opB);
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// C -= P P^T restricted to the block columns [c0, c1) (and the rows from c0 down) of the trailing matrix that
+// starts at block kend; P = the split panel (row 0 of `panel` / the operands = global block row kend).
+static int potrf_update(void* stream, float* A, int64_t lda, int nblk, int kend, int c0, int c1, const float* panel,
+                        int64_t ldp, int W, const LinalgWs& w) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long off = static_cast<long long>(c0 - kend) * TS;      // first operand row of this update
+  const long long ncols = static_cast<long long>(c1 - c0) * TS;
+  const long long nrows = static_cast<long long>(nblk - c0) * TS;
+  float* C = A + static_cast<long long>(c0) * TS * (lda + 1);
+  // the diagonal of the update is a sum of squares: exact in fp32 (the tensor-core accumulator is biased there)
+  exact_diag_kernel<<<static_cast<int>(ceil_div(ncols * 32, 256)), 256, 0, st>>>(C, lda, panel + off * ldp, ldp, ncols,
+                                                                             W, -1.f, w.dsave + off);
+  SAB_CHECK_CUDA(cudaGetLastError());
+  if (int rc = tc_gemm_nt(stream, w.opA + off * 3 * W, nrows, 3 * W, w.opB + off * 3 * W, ncols, 3 * W, 3 * W, C, lda,
+                          -tc_gain(W), w.hdr + 2, 1.f, 1))
+    return rc;
+  restore_diag_kernel<<<static_cast<int>(ceil_div(ncols, 256)), 256, 0, st>>>(C, lda, ncols, w.dsave + off);
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sa_potrf(void* stream, float* A, int64_t M, int64_t lda, float* invdiag, int* info,
+                        void* workspace, int64_t workspace_bytes) {
+  SAB_REQUIRE_MAT(M, lda, A);
+  SAB_REQUIRE(invdiag != nullptr && info != nullptr, "invdiag / info must not be NULL");
+  SAB_REQUIRE_WS(M, workspace, workspace_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nblk = static_cast<int>(M / TS);
+  const bool tensor = use_tensor_path();
+  const int nbb = tensor ? outer_blocks() : nblk;  // SIMT: classic right-looking (one "outer panel")
+  const LinalgWs w = carve(workspace, M);
+  if (int rc = potrf_begin(st, A, M, lda, info, w, tensor)) return rc;
   for (int k0 = 0; k0 < nblk; k0 += nbb) {
     const int kend = k0 + nbb < nblk ? k0 + nbb : nblk;
-    // ---- factor the outer panel (columns [k0, kend) x all rows below) with 128-wide fp32 SIMT steps
-    for (int k = k0; k < kend; ++k) {
-      diag_factor_kernel<<<1, 256, dsmem, st>>>(A, lda, k, invdiag, info);
-      const int rem = nblk - k - 1;
-      if (rem == 0) break;
-      sgemm_kernel<MODE_PANEL><<<rem, 256, 0, st>>>(A, lda, invdiag + static_cast<long long>(k) * TS * TS, TS, k,
-                                                    nblk, 0.f, 0.f);
-      const int jlim = (tensor ? kend : nblk) - k - 1;  // block columns right of k still inside the panel
-      if (jlim >= rem)
-        sgemm_kernel<MODE_SYRK><<<rem * (rem + 1) / 2, 256, 0, st>>>(A, lda, nullptr, 0, k, nblk,
-                                                                     static_cast<float>(jlim), 0.f);
-      else if (jlim > 0)
-        sgemm_kernel<MODE_SYRK><<<rem * jlim, 256, 0, st>>>(A, lda, nullptr, 0, k, nblk, static_cast<float>(jlim), 0.f);
-    }
+    if (int rc = potrf_panel(st, A, lda, invdiag, info, nblk, k0, kend, tensor ? kend : nblk)) return rc;
     // ---- trailing update C -= P P^T on the tensor cores, P = the finished panel below row kend*128
     if (tensor && kend < nblk) {
       const long long rows = static_cast<long long>(nblk - kend) * TS;
       const int W = (kend - k0) * TS;
-      float* panel = A + static_cast<long long>(kend) * TS * lda + static_cast<long long>(k0) * TS;
-      float* C = A + static_cast<long long>(kend) * TS * (lda + 1);
-      exact_diag_kernel<<<static_cast<int>(ceil_div(rows * 32, 256)), 256, 0, st>>>(C, lda, panel, lda, rows, W, -1.f,
-                                                                                w.dsave);
-      split_f16_kernel<<<static_cast<int>(ceil_div(rows * (W / 8), 256)), 256, 0, st>>>(panel, lda, rows, W, 0, 0, w.hdr,
-                                                                                     w.opA, w.opB);
-      SAB_CHECK_CUDA(cudaGetLastError());
-      if (int rc = tc_gemm_nt(stream, w.opA, rows, 3 * W, w.opB, rows, 3 * W, 3 * W, C, lda, -tc_gain(W), w.hdr + 2,
-                              1.f, 1))
-        return rc;
-      restore_diag_kernel<<<static_cast<int>(ceil_div(rows, 256)), 256, 0, st>>>(C, lda, rows, w.dsave);
+      const float* panel = A + static_cast<long long>(kend) * TS * lda + static_cast<long long>(k0) * TS;
+      if (int rc = potrf_split(st, panel, lda, rows, W, w)) return rc;
+      if (int rc = potrf_update(stream, A, lda, nblk, kend, kend, nblk, panel, lda, W, w)) return rc;
     }
   }
-  SAB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int sa_potrf_outer_blocks(void) { return use_tensor_path() ? outer_blocks() : 0; }
+
+extern "C" int sa_potrf_begin(void* stream, const float* A, int64_t M, int64_t lda, int* info, void* workspace,
+                              int64_t workspace_bytes) {
+  SAB_REQUIRE_MAT(M, lda, A);
+  SAB_REQUIRE(info != nullptr, "info must not be NULL");
+  SAB_REQUIRE(use_tensor_path(), "the panel-wise factorisation needs the tensor-core path");
+  SAB_REQUIRE_WS(M, workspace, workspace_bytes);
+  return potrf_begin(static_cast<cudaStream_t>(stream), A, M, lda, info, carve(workspace, M), true);
+}
+
+extern "C" int sa_potrf_panel(void* stream, float* A, int64_t M, int64_t lda, float* invdiag, int* info, int k0,
+                              int kend) {
+  SAB_REQUIRE_MAT(M, lda, A);
+  const int nblk = static_cast<int>(M / TS);
+  SAB_REQUIRE(invdiag != nullptr && info != nullptr && 0 <= k0 && k0 < kend && kend <= nblk &&
+                  kend - k0 <= 1024 / TS,
+              "bad panel [%d, %d) of %d blocks", k0, kend, nblk);
+  return potrf_panel(static_cast<cudaStream_t>(stream), A, lda, invdiag, info, nblk, k0, kend, kend);
+}
+
+extern "C" int sa_potrf_split(void* stream, int64_t M, const float* panel, int64_t ldp, int64_t rows, int W,
+                              void* workspace, int64_t workspace_bytes) {
+  SAB_REQUIRE(M > 0 && M % TS == 0 && panel != nullptr && rows > 0 && rows % TS == 0 && rows < M && W > 0 &&
+                  W % TS == 0 && W <= outer_blocks() * TS && ldp >= W && ldp % 4 == 0 &&
+                  (reinterpret_cast<uintptr_t>(panel) & 15) == 0,
+              "bad panel operand (rows=%lld W=%d ldp=%lld)", (long long)rows, W, (long long)ldp);
+  SAB_REQUIRE_WS(M, workspace, workspace_bytes);
+  return potrf_split(static_cast<cudaStream_t>(stream), panel, ldp, rows, W, carve(workspace, M));
+}
+
+extern "C" int sa_potrf_update(void* stream, float* A, int64_t M, int64_t lda, int kend, int c0, int c1,
+                               const float* panel, int64_t ldp, int W, void* workspace, int64_t workspace_bytes) {
+  SAB_REQUIRE_MAT(M, lda, A);
+  const int nblk = static_cast<int>(M / TS);
+  SAB_REQUIRE(panel != nullptr && 0 < kend && kend <= c0 && c0 < c1 && c1 <= nblk && W > 0 && W % TS == 0 &&
+                  W <= outer_blocks() * TS && ldp >= W,
+              "bad update: kend=%d columns [%d, %d) of %d blocks, W=%d", kend, c0, c1, nblk, W);
+  SAB_REQUIRE_WS(M, workspace, workspace_bytes);
+  return potrf_update(stream, A, lda, nblk, kend, c0, c1, panel, ldp, W, carve(workspace, M));
 }
 
 extern "C" int sa_ltl_part(void* stream, const float* L, int64_t M, int64_t ldl, float* G, int64_t ldg,

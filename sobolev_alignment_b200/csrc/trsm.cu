@@ -24,10 +24,10 @@
 // interleaved), so heavy block rows are spread over many CTAs and the chain never waits for a CTA that
 // is not resident.  Roles inside a CTA:
 //   warp 8  (tile producer)    draws tickets, queues item descriptors, streams half tiles (32 KB
-//                              `cp.async.bulk`, mbarrier complete_tx) through a 5-slot ring
+//                              `cp.async.bulk`, mbarrier complete_tx) through a 6-slot ring
 //   warp 9  (x producer)       waits for the published-flag of each dependency block (ld.acquire.gpu)
 //                              and bulk-copies its converted x (fp16 hi/lo, [column][k], swizzled, with
-//                              its power-of-two scale in the trailer) into a 3-slot ring
+//                              its power-of-two scale in the trailer) into a 2-slot ring
 //   warps 0-7 (consumers)      16 output rows each: ldmatrix + mma.sync.m16n8k16 (hi hi + lo hi + hi lo),
 //                              fp32 accumulators in registers; the publisher of a block converts its x
 //                              ONCE for all later consumers.
@@ -52,8 +52,8 @@ constexpr int TS = 128;
 constexpr int TILE_BYTES = TS * TS * 4;      // 64 KB: hi + lo
 constexpr int HALF_BYTES = TILE_BYTES / 2;   // rows 0-63 / 64-127 of the stored tile
 constexpr int ROW_BYTES = 512;
-constexpr int NSLOT = 5;                     // half-tile ring
-constexpr int NXSLOT = 3;                    // converted-x ring
+constexpr int NSLOT = 6;                     // half-tile ring: the last three tiles of a finishing row all fit
+constexpr int NXSLOT = 2;                    // converted-x ring (one slot per tile; also the inverse product's operand)
 constexpr int IQ = 4;                        // item queue depth
 constexpr int NCONS = 8;                     // consumer warps
 constexpr int THREADS = (NCONS + 2) * 32;
@@ -77,6 +77,7 @@ struct Params {
   int* sync;        // [0] ticket | [SYNC_HDR + (2 j) nblk + blk] published | [SYNC_HDR + (2 j + 1) nblk + row] partial count
   float* partial;   // [njobs][nblk][128 x 32]
   uint8_t* xhat;    // [njobs][nblk][xhat_bytes]
+  long long* trace; // developer tool (option SAB_TRSM_TRACE_PTR): 8 globaltimer stamps per block of job 0
 };
 
 struct Item {
@@ -96,11 +97,12 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // bounded spin: a scheduling bug must surface as a trapped kernel, never as a hung GPU
-__device__ __forceinline__ void wait_flag_ge(const int* f, int want, int what) {
+__device__ __forceinline__ void wait_flag_ge(const int* f, int want, int what, unsigned backoff_ns) {
   if (ld_acquire_gpu(f) >= want) return;
   unsigned spins = 0;
   unsigned long long t0 = 0;
   while (ld_acquire_gpu(f) < want) {
+    if (backoff_ns) __nanosleep(backoff_ns);
     if ((++spins & 0x3FFu) == 0) {
       const unsigned long long now = global_timer_ns();
       if (t0 == 0) t0 = now;
@@ -241,8 +243,7 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* ring = smem_raw;                                    // NSLOT x 32 KB
   uint8_t* xring = ring + NSLOT * HALF_BYTES;                  // NXSLOT x XB (XB is a multiple of 16)
-  uint8_t* own = xring + NXSLOT * XB;                          // the CTA's own converted operand (inverse product)
-  Smem& sm = *reinterpret_cast<Smem*>(own + XB);
+  Smem& sm = *reinterpret_cast<Smem*>(xring + NXSLOT * XB);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = p.nblk, CH = p.chunk, dp = p.dp;
 
@@ -313,6 +314,9 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
     }
   } else if (warp == NCONS + 1) {
     // ================================ x producer ================================
+    // One slot of the x ring per tile, in tile order.  Dependency / W tiles: wait for the block's published
+    // flag, bulk-copy its converted x.  Inverse tile: the slot is handed to the consumers empty (they build
+    // the operand b_c - sum themselves).
     int xg = 0, nq = 0;
     for (;;) {
       const int qs = nq % IQ;
@@ -325,21 +329,26 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
       const int nt = ntiles_of(it);
       const int* pub = p.sync + SYNC_HDR + (2 * it.job) * nblk;
       const uint8_t* xh = p.xhat + static_cast<long long>(it.job) * nblk * XB;
-      for (int i = 0; i < nt; ++i) {
+      for (int i = 0; i < nt; ++i, ++xg) {
         const int kd = kind_of(it, i);
-        if (kd == KIND_INV) continue;
-        const int dep = kd == KIND_DEP ? it.k0 + i : it.c - 1;   // chain index of the block whose x is needed
-        const int b = blk_of(dep);
         const int s = xg % NXSLOT;
         mbar_wait(smem_u32(&sm.xempty[s]), ((xg / NXSLOT) & 1) ^ 1);
         if (lane == 0) {
-          wait_flag_ge(pub + b, 1, b);
-          fence_proxy_async_all();   // the block was written through the generic proxy of another SM
-          mbar_arrive_expect_tx(smem_u32(&sm.xfull[s]), XB);
-          bulk_load_1d(smem_u32(xring + s * XB), xh + static_cast<long long>(b) * XB, XB, smem_u32(&sm.xfull[s]));
+          if (kd == KIND_INV) {
+            mbar_arrive(smem_u32(&sm.xfull[s]));
+          } else {
+            const int dep = kd == KIND_DEP ? it.k0 + i : it.c - 1;   // chain index of the block whose x is needed
+            const int b = blk_of(dep);
+            // only the W tile of a finishing row sits on the chain: everything else polls politely
+            wait_flag_ge(pub + b, 1, b, kd == KIND_W ? 0u : 400u);
+            fence_proxy_async_all();   // the block was written through the generic proxy of another SM
+            if (p.trace != nullptr && kd == KIND_W && it.job == 0)
+              p.trace[static_cast<long long>(blk_of(it.c)) * 8 + 0] = static_cast<long long>(global_timer_ns());
+            mbar_arrive_expect_tx(smem_u32(&sm.xfull[s]), XB);
+            bulk_load_1d(smem_u32(xring + s * XB), xh + static_cast<long long>(b) * XB, XB, smem_u32(&sm.xfull[s]));
+          }
         }
         __syncwarp();
-        ++xg;
       }
     }
   } else {
@@ -347,9 +356,9 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
     const int g8 = lane >> 2, t4 = lane & 3;
     const int m0 = warp * 16;                  // output rows of this warp inside the block
     const int myhalf = warp >> 2;              // forward: which stored half holds this warp's rows
-    int T = 0;                                 // tiles consumed (stage counter = 2 T + half)
-    int xg = 0, nq = 0, nred = 0;
-    const uint32_t ring_a = smem_u32(ring), xring_a = smem_u32(xring), own_a = smem_u32(own);
+    int T = 0;                                 // tiles consumed (stage counter = 2 T + half; x slot = T % NXSLOT)
+    int nq = 0, nred = 0;
+    const uint32_t ring_a = smem_u32(ring), xring_a = smem_u32(xring);
 
     // block-wide max of |v| over the 128 x NP operand held in fragment layout
     auto block_max = [&](float m) {
@@ -371,6 +380,22 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
       sc = ldexpf(1.f, 14 - e);
       return ldexpf(1.f, e - 14);
     };
+    // fragment (fp32, [128 x NP]) -> converted operand (fp16 hi / lo, [n][k] swizzled) in shared memory
+    auto store_operand = [&](uint8_t* dst, const float (&v)[NB8][4], float sc) {
+#pragma unroll
+      for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int n = nb * 8 + 2 * t4 + (q & 1), k = m0 + g8 + (q >> 1) * 8;
+          const float sv = v[nb][q] * sc;
+          const __half h = __float2half_rn(sv);
+          *reinterpret_cast<__half*>(dst + xoff(n, k)) = h;
+          *reinterpret_cast<__half*>(dst + NP * 256 + xoff(n, k)) = __float2half_rn(sv - __half2float(h));
+        }
+    };
+    auto stamp = [&](int blk, int i) {
+      if (p.trace != nullptr && threadIdx.x == 0) p.trace[static_cast<long long>(blk) * 8 + i] = static_cast<long long>(global_timer_ns());
+    };
 
     for (;;) {
       const int qs = nq % IQ;
@@ -383,10 +408,12 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
       const Job& J = p.job[it.job];
       const int blk = blk_of(it.c);
       const int nt = ntiles_of(it);
+      const bool tr = p.trace != nullptr && it.fin && it.job == 0;
       int* pub = p.sync + SYNC_HDR + (2 * it.job) * nblk;
       int* pcnt = p.sync + SYNC_HDR + (2 * it.job + 1) * nblk;
       float* part = p.partial + (static_cast<long long>(it.job) * nblk + it.c) * (TS * 32);
       const long long frow = static_cast<long long>(blk) * TS + m0 + g8;   // global row of fragment rows (+8)
+      if (tr) stamp(blk, 7);
 
       float S[NB8][4], U[NB8][4];
 #pragma unroll
@@ -397,7 +424,7 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
       // S += the partial sum the previous item of this block row left behind (fixed order: item q-1 before q)
       auto add_previous_partial = [&]() {
         if (it.q == 0) return;
-        wait_flag_ge(pcnt + it.c, it.q, -it.c);
+        wait_flag_ge(pcnt + it.c, it.q, -it.c, 0u);
 #pragma unroll
         for (int nb = 0; nb < NB8; ++nb) {
           const int cc = nb * 8 + 2 * t4;
@@ -406,55 +433,63 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
           S[nb][0] += v0.x; S[nb][1] += v0.y; S[nb][2] += v1.x; S[nb][3] += v1.y;
         }
       };
+      // right-hand side fragment b_c (+ lambda V): job 0 reads its own input, job 1 the block job 0 published
+      float bf[NB8][4];
+      auto load_rhs = [&]() {
+#pragma unroll
+        for (int nb = 0; nb < NB8; ++nb) {
+          const int cc = nb * 8 + 2 * t4;
+          float2 b0 = make_float2(0.f, 0.f), b1 = make_float2(0.f, 0.f);
+          if (cc < dp) {
+            b0 = __ldcg(reinterpret_cast<const float2*>(J.rhs + frow * dp + cc));
+            b1 = __ldcg(reinterpret_cast<const float2*>(J.rhs + (frow + 8) * dp + cc));
+            if (J.V != nullptr) {
+              const float2 a0 = *reinterpret_cast<const float2*>(J.V + frow * dp + cc);
+              const float2 a1 = *reinterpret_cast<const float2*>(J.V + (frow + 8) * dp + cc);
+              b0.x = fmaf(J.lambda, a0.x, b0.x); b0.y = fmaf(J.lambda, a0.y, b0.y);
+              b1.x = fmaf(J.lambda, a1.x, b1.x); b1.y = fmaf(J.lambda, a1.y, b1.y);
+            }
+          }
+          bf[nb][0] = b0.x; bf[nb][1] = b0.y; bf[nb][2] = b1.x; bf[nb][3] = b1.y;
+        }
+      };
+      // a finishing row fetches what does not depend on the chain up front: its earlier partial sum (written
+      // a whole chunk column ago) and, for job 0, its right-hand side
+      if (it.fin) {
+        add_previous_partial();
+        if (it.job == 0) load_rhs();
+      }
 
       for (int i = 0; i < nt; ++i, ++T) {
         const int kd = kind_of(it, i);
-        uint32_t xop;
+        const int xs = T % NXSLOT;
+        uint8_t* xslot = xring + xs * XB;
+        const uint32_t xop = xring_a + xs * XB;
         float xinv;
+        mbar_wait(smem_u32(&sm.xfull[xs]), (T / NXSLOT) & 1);
         if (kd == KIND_INV) {
-          // operand = b_c - (sum of all eliminated dependencies), converted by this CTA
-          add_previous_partial();
-          if (it.job == 1) wait_flag_ge(p.sync + SYNC_HDR + blk, 1, blk);   // job 0 has published this block
+          // operand = b_c - (sum of all eliminated dependencies), converted by this CTA into the handed-over slot
+          if (it.job == 1) {
+            wait_flag_ge(p.sync + SYNC_HDR + blk, 1, blk, 0u);   // job 0 has published this block
+            load_rhs();
+          }
           float v[NB8][4];
           float m = 0.f;
-#pragma unroll
-          for (int nb = 0; nb < NB8; ++nb) {
-            const int cc = nb * 8 + 2 * t4;
-            float2 b0 = make_float2(0.f, 0.f), b1 = make_float2(0.f, 0.f);
-            if (cc < dp) {
-              b0 = __ldcg(reinterpret_cast<const float2*>(J.rhs + frow * dp + cc));
-              b1 = __ldcg(reinterpret_cast<const float2*>(J.rhs + (frow + 8) * dp + cc));
-              if (J.V != nullptr) {
-                const float2 a0 = *reinterpret_cast<const float2*>(J.V + frow * dp + cc);
-                const float2 a1 = *reinterpret_cast<const float2*>(J.V + (frow + 8) * dp + cc);
-                b0.x = fmaf(J.lambda, a0.x, b0.x); b0.y = fmaf(J.lambda, a0.y, b0.y);
-                b1.x = fmaf(J.lambda, a1.x, b1.x); b1.y = fmaf(J.lambda, a1.y, b1.y);
-              }
-            }
-            v[nb][0] = b0.x - S[nb][0]; v[nb][1] = b0.y - S[nb][1];
-            v[nb][2] = b1.x - S[nb][2]; v[nb][3] = b1.y - S[nb][3];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) m = fmaxf(m, fabsf(v[nb][q]));
-          }
-          float sc;
-          xinv = pick_scale(block_max(m), sc);
 #pragma unroll
           for (int nb = 0; nb < NB8; ++nb)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const int n = nb * 8 + 2 * t4 + (q & 1), k = m0 + g8 + (q >> 1) * 8;
-              const float sv = v[nb][q] * sc;
-              const __half h = __float2half_rn(sv);
-              *reinterpret_cast<__half*>(own + xoff(n, k)) = h;
-              *reinterpret_cast<__half*>(own + NP * 256 + xoff(n, k)) = __float2half_rn(sv - __half2float(h));
+              v[nb][q] = bf[nb][q] - S[nb][q];
+              m = fmaxf(m, fabsf(v[nb][q]));
             }
+          float sc;
+          xinv = pick_scale(block_max(m), sc);
+          store_operand(xslot, v, sc);
+          fence_proxy_async_smem();   // the slot is refilled by cp.async.bulk later: order these generic writes before it
           consumer_bar();
-          xop = own_a;
         } else {
-          const int xs = xg % NXSLOT;
-          mbar_wait(smem_u32(&sm.xfull[xs]), (xg / NXSLOT) & 1);
-          xop = xring_a + xs * XB;
-          xinv = *reinterpret_cast<const float*>(xring + xs * XB + 2 * NP * 256);
+          xinv = *reinterpret_cast<const float*>(xslot + 2 * NP * 256);
+          if (tr && kd == KIND_W) stamp(blk, 1);
         }
         float acc[NB8][4], acx[NB8][4];
 #pragma unroll
@@ -464,6 +499,7 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
         if (!TRANS) {
           const int g = 2 * T + myhalf, s = g % NSLOT;
           mbar_wait(smem_u32(&sm.full[s]), (g / NSLOT) & 1);
+          if (tr && kd == KIND_W) stamp(blk, 2);
           mma_steps<NB8, false>(ring_a + s * HALF_BYTES, xop, 0, 8, m0 - myhalf * 64, acc, acx);
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&sm.empty[s]));
@@ -472,15 +508,16 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
           for (int h = 0; h < 2; ++h) {
             const int g = 2 * T + h, s = g % NSLOT;
             mbar_wait(smem_u32(&sm.full[s]), (g / NSLOT) & 1);
+            if (tr && kd == KIND_W && h == 1) stamp(blk, 2);
             mma_steps<NB8, true>(ring_a + s * HALF_BYTES, xop, h * 4, 4, m0, acc, acx);
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&sm.empty[s]));
           }
         }
-        if (kd != KIND_INV) {
+        // the x slot of a finishing row's LAST tile is kept: it stages the converted x_c for publication
+        if (!(it.fin && i == nt - 1)) {
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&sm.xempty[xg % NXSLOT]));
-          ++xg;
+          if (lane == 0) mbar_arrive(smem_u32(&sm.xempty[xs]));
         }
         const float r = __ldg(J.scales + kd) * xinv;
 #pragma unroll
@@ -510,6 +547,7 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
         }
       } else {
         // x_c: fp32 result + the converted operand every later block row will use
+        if (tr) stamp(blk, 3);
         float m = 0.f;
 #pragma unroll
         for (int nb = 0; nb < NB8; ++nb) {
@@ -522,24 +560,27 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
           for (int q = 0; q < 4; ++q) m = fmaxf(m, fabsf(U[nb][q]));
         }
         float sc;
-        const float inv = pick_scale(block_max(m), sc);
+        const float inv = pick_scale(block_max(m), sc);   // (its barrier: every warp is done reading the slot)
+        if (tr) stamp(blk, 4);
+        const int xs = (T - 1) % NXSLOT;
+        uint8_t* stage = xring + xs * XB;
+        store_operand(stage, U, sc);
+        if (threadIdx.x == 0) *reinterpret_cast<float*>(stage + 2 * NP * 256) = inv;
+        fence_proxy_async_smem();
+        consumer_bar();
+        // coalesced copy of the staged block to global memory (16 bytes per thread and step)
         uint8_t* xh = p.xhat + (static_cast<long long>(it.job) * nblk + blk) * XB;
-#pragma unroll
-        for (int nb = 0; nb < NB8; ++nb)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int n = nb * 8 + 2 * t4 + (q & 1), k = m0 + g8 + (q >> 1) * 8;
-            const float sv = U[nb][q] * sc;
-            const __half h = __float2half_rn(sv);
-            *reinterpret_cast<__half*>(xh + xoff(n, k)) = h;
-            *reinterpret_cast<__half*>(xh + NP * 256 + xoff(n, k)) = __float2half_rn(sv - __half2float(h));
-          }
-        if (threadIdx.x == 0) *reinterpret_cast<float*>(xh + 2 * NP * 256) = inv;
+        for (int o = threadIdx.x * 16; o < XB; o += NCONS * 32 * 16)
+          __stcg(reinterpret_cast<uint4*>(xh + o), *reinterpret_cast<const uint4*>(stage + o));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm.xempty[xs]));
+        if (tr) stamp(blk, 5);
         consumer_bar();
         if (threadIdx.x == 0) {
           __threadfence();
           fence_proxy_async_all();
           st_release_gpu(pub + blk, 1);
+          if (tr) stamp(blk, 6);
         }
       }
     }
@@ -694,7 +735,7 @@ static long long tri_tiles(long long nblk) { return nblk * (nblk - 1) / 2; }
 
 template <int NB8>
 static int launch_solve(cudaStream_t st, const Params& p, int transpose) {
-  const int smem = NSLOT * HALF_BYTES + (NXSLOT + 1) * xhat_bytes(NB8) + static_cast<int>(sizeof(Smem));
+  const int smem = NSLOT * HALF_BYTES + NXSLOT * xhat_bytes(NB8) + static_cast<int>(sizeof(Smem));
   const long long grid = p.nitems < sm_count() ? p.nitems : sm_count();
   auto go = [&](auto kern) -> int {
     SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -783,6 +824,10 @@ static int solve_jobs(cudaStream_t st, Params& p, int64_t M, int dp, int transpo
   p.partial = reinterpret_cast<float*>(ws + off);
   off += 2ll * nblk * TS * 32 * 4;
   p.xhat = ws + off;
+  {
+    char tp[64];
+    p.trace = option("SAB_TRSM_TRACE_PTR", tp) ? reinterpret_cast<long long*>(std::strtoull(tp, nullptr, 0)) : nullptr;
+  }
   SAB_CHECK_CUDA(cudaMemsetAsync(p.sync, 0, (SYNC_HDR + 4ll * nblk) * 4, st));
   switch ((dp + 7) / 8) {
     case 1: return launch_solve<1>(st, p, transpose);

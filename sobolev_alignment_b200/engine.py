@@ -157,6 +157,11 @@ class CudaOps:
         return nat.kdense(spec.kid, spec.kscale(frame.gscale), A, B, out, symmetric)
 
     potrf = staticmethod(nat.potrf)
+    potrf_outer_blocks = staticmethod(nat.potrf_outer_blocks)
+    potrf_begin = staticmethod(nat.potrf_begin)
+    potrf_panel = staticmethod(nat.potrf_panel)
+    potrf_split = staticmethod(nat.potrf_split)
+    potrf_update = staticmethod(nat.potrf_update)
     ltl = staticmethod(nat.ltl)
     add_diag = staticmethod(nat.add_diag)
     trsm_pack = staticmethod(nat.trsm_pack)

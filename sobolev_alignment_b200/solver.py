@@ -23,6 +23,7 @@ import time
 
 import torch
 
+from . import distributed
 from .engine import KernelSpec, pad_cols
 
 TILE = 128
@@ -49,12 +50,24 @@ class Comm:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t
 
+    def broadcast_async(self, t: torch.Tensor, src: int):
+        """Start a broadcast of `t` from group rank `src`; returns a handle whose wait() orders the current stream."""
+        if not (self.enabled and self.world > 1):
+            return _Done()
+        gsrc = self.dist.get_global_rank(self.group, src) if self.group is not None else src
+        return self.dist.broadcast(t, src=gsrc, group=self.group, async_op=True)
+
     def sum_int(self, v: int, device) -> int:
         if not (self.enabled and self.world > 1):
             return v
         t = torch.tensor([v], dtype=torch.int64, device=device)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return int(t.item())
+
+
+class _Done:
+    def wait(self):
+        return True
 
 
 class Preconditioner:
@@ -86,9 +99,8 @@ class Preconditioner:
         self._finish(held, penalty, comm if distributed else None)
 
     def _potrf(self, A, inv, info, comm):
-        dist_potrf = getattr(self.ops, "potrf_distributed", None)
-        if comm is not None and dist_potrf is not None:
-            dist_potrf(A, inv, info, comm)
+        if comm is not None and hasattr(self.ops, "potrf_panel"):
+            distributed.potrf(self.ops, A, inv, info, comm)     # outer panels dealt out over the ranks
         else:
             self.ops.potrf(A, inv, info)
 

@@ -83,6 +83,29 @@ class CpuOps:
         L = torch.linalg.cholesky(torch.tril(A) + torch.tril(A, -1).T)
         A.copy_(L)
 
+    # the factorisation in steps (outer panels dealt out over the ranks); one 128-block per outer panel here
+    def potrf_outer_blocks(self):
+        return 1
+
+    def potrf_begin(self, A, info):
+        info.zero_()
+
+    def potrf_panel(self, A, invdiag, info, k0, kend):
+        a, b = k0 * 128, kend * 128
+        D = torch.tril(A[a:b, a:b])
+        L = torch.linalg.cholesky(D + torch.tril(D, -1).T)
+        A[a:b, a:b] = L
+        if b < A.shape[0]:
+            A[b:, a:b] = torch.linalg.solve_triangular(L, A[b:, a:b].T.contiguous(), upper=False).T
+
+    def potrf_split(self, m, panel, W):
+        pass
+
+    def potrf_update(self, A, kend, c0, c1, panel, W):
+        off, ncols = (c0 - kend) * 128, (c1 - c0) * 128
+        P = panel[off:]
+        A[c0 * 128:, c0 * 128: c1 * 128] -= P @ P[:ncols].T
+
     def ltl(self, L, G, alpha, beta):
         Lt = torch.tril(L)
         G.copy_(alpha * (Lt.T @ Lt) + beta * torch.eye(L.shape[0], dtype=L.dtype))

@@ -415,7 +415,11 @@ def test_paired_solves_match_two_single_solves(cuda_ops, M, dp, chunk, sab_optio
             assert relerr(xa, ra) < 2e-5 and relerr(xb, rb) < 2e-5
             pa, pb = B.clone(), torch.full_like(B, float("nan"))
             nat.trsm_pair(Fa, Fb, pa, pb, Vt, lam, tr)
-            assert torch.equal(pa, xa) and torch.equal(pb, xb)   # fixed summation order: bit identical
+            assert torch.equal(pa, xa)                            # fixed summation order: bit identical
+            if Vt is None:
+                assert torch.equal(pb, xb)
+            else:                                                 # the pair forms xa + lam V with one fma
+                assert relerr(pb, xb.double()) < FP32_TOL
             # and reproducible run to run (no atomics, no order dependence on the CTA schedule)
             qa, qb = B.clone(), torch.full_like(B, float("nan"))
             nat.trsm_pair(Fa, Fb, qa, qb, Vt, lam, tr)
@@ -527,3 +531,43 @@ def test_cg_vector_kernels(cuda_ops):
     nat.cg_update(P.cuda(), Q.cuda(), Xd, Rd, rs_old.cuda(), pAp.cuda(), 1e-7, rs_new, cgs, hist_row=3, tol=1e-7)
     nat.cg_direction(Rd, Pd, rs_new, rs_old.cuda(), 1e-7, cgs)
     assert torch.equal(Xf, Xd) and torch.equal(Pf, Pd)
+
+
+def test_stepwise_cholesky_matches_potrf(cuda_ops, sab_option):
+    """
+    sa_potrf_begin / _panel / _split / _update (what the row-sharded solver strings together over NCCL):
+    applied panel by panel with the trailing update cut into per-panel column ranges -- the way two ranks
+    would share it -- they reproduce sa_potrf.
+    """
+    from sobolev_alignment_b200 import _native as nat
+
+    sab_option("SAB_CHOL_NB", "256")
+    M = 2304                                           # 18 blocks, 9 outer panels of 2 blocks
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Z = torch.randn(M, 24, device="cuda", generator=g)
+    K = torch.cdist(Z, Z).mul_(-1.0 / 6.0).exp_()
+    K.diagonal().add_(1e-2)
+    ref, inv_ref = K.clone(), torch.empty(M // 128, 128, 128, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    nat.potrf(ref, inv_ref, info)
+    assert int(info) == 0
+    A, inv = K.clone(), torch.empty(M // 128, 128, 128, device="cuda")
+    nb, nblk = nat.potrf_outer_blocks(), M // 128
+    assert nb == 2
+    nat.potrf_begin(A, info)
+    for k0 in range(0, nblk, nb):
+        kend = min(nblk, k0 + nb)
+        nat.potrf_panel(A, inv, info, k0, kend)
+        if kend == nblk:
+            break
+        W = (kend - k0) * 128
+        panel = A[k0 * 128:, k0 * 128: kend * 128].contiguous()      # what a non-owner receives
+        below = panel[W:]
+        nat.potrf_split(M, below, W)
+        for c0 in range(kend, nblk, nb):                             # one update per outer panel still to come
+            nat.potrf_update(A, kend, c0, min(nblk, c0 + nb), below, W)
+    assert int(info) == 0
+    assert relerr(torch.tril(A), torch.tril(ref).double()) < 1e-6
+    assert relerr(inv, inv_ref.double()) < 1e-5
+    Lref = torch.linalg.cholesky(K.double())
+    assert relerr(torch.tril(A), Lref) < FP32_TOL

@@ -221,4 +221,5 @@ def test_kmv_near_duplicate_rows(cuda_ops, kernel, nu):
     Kd = cuda_ops.zeros(X.shape[0], M)
     cuda_ops.kdense(spec, frame, Xp, Cp, Kd)
     Kref = fo.kernel_matrix(X, C, kernel, 10.0, nu)
-    assert float((Kd.cpu().double() - Kref).abs().max()) < 2e-4
+    # entries: fp16 operands put ~3e-4 of absolute error on K at p = 1000 (it averages out in K v)
+    assert float((Kd.cpu().double() - Kref).abs().max()) < 6e-4

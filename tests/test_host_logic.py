@@ -274,3 +274,76 @@ def test_row_sharded_fit_world2_gloo(tmp_path):
     ref = fo.falkon_fit(X, Y, X[idx], "laplacian", 7.0, 1e-4)
     assert relerr(r0["alpha"], ref) < 1e-4
     assert relerr(r0["pred"], fo.falkon_predict(Xv, X[idx], ref, "laplacian", 7.0)) < 1e-4
+
+
+# ---------------------------------------------------------------------------- distributed Cholesky over gloo
+def _potrf_rank_main(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    from sobolev_alignment_b200 import distributed
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        M = 7 * 128                                   # 7 outer panels (one block each on the stand-in engine)
+        g = torch.Generator().manual_seed(3)
+        Z = torch.randn(M, 12, generator=g, dtype=torch.float64)
+        K = torch.exp(-torch.cdist(Z, Z) / 4.0) + 1e-2 * torch.eye(M, dtype=torch.float64)
+        ops = CpuOps()
+        A = K.clone()
+        inv = ops.empty(M // 128, 128, 128)
+        info = torch.zeros(1, dtype=torch.int32)
+        distributed.potrf(ops, A, inv, info, Comm(None, enabled=True))
+        torch.save({"L": torch.tril(A), "K": K, "info": info}, os.path.join(out_dir, f"potrf{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_potrf_gloo(tmp_path, world):
+    """Outer panels dealt out over the ranks, panels broadcast with one step of look-ahead: every rank ends with the full factor."""
+    port = _free_port()
+    mp.spawn(_potrf_rank_main, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(os.path.join(tmp_path, f"potrf{r}.pt")) for r in range(world)]
+    ref = torch.linalg.cholesky(outs[0]["K"])
+    for o in outs:
+        assert int(o["info"]) == 0
+        assert torch.equal(o["L"], outs[0]["L"])            # bit-identical on all ranks
+        assert relerr(o["L"], ref) < 1e-12
+
+
+def _sharded_large_m_rank_main(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        X, Xv, W, Y, Yv = krr_test_data(seed=8, n=1501, p=24, d=3)
+        bounds = np.linspace(0, X.shape[0], world + 1).astype(int)
+        Xl, Yl = X[bounds[rank]:bounds[rank + 1]], Y[bounds[rank]:bounds[rank + 1]]
+        falkon_models.CudaOps = CpuOps
+        clf = Falkon(kernel=LaplacianKernel(sigma=7.0), penalty=1e-4, M=600, seed=5,
+                     options=FalkonOptions(row_sharded=True))      # 5 outer panels per factorisation
+        clf.fit(Xl, Yl)
+        torch.save({"alpha": clf.alpha_, "pred": clf.predict(Xv)}, os.path.join(out_dir, f"big{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_fit_with_distributed_preconditioner_gloo(tmp_path):
+    """The row-sharded fit with M large enough that both Cholesky factorisations run panel-distributed."""
+    world = 2
+    port = _free_port()
+    mp.spawn(_sharded_large_m_rank_main, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(os.path.join(tmp_path, "big0.pt"))
+    r1 = torch.load(os.path.join(tmp_path, "big1.pt"))
+    assert torch.equal(r0["alpha"], r1["alpha"])
+    X, Xv, W, Y, Yv = krr_test_data(seed=8, n=1501, p=24, d=3)
+    idx = np.sort(np.random.default_rng(5).choice(1501, size=600, replace=False))
+    ref = fo.falkon_fit(X, Y, X[idx], "laplacian", 7.0, 1e-4)
+    assert relerr(r0["alpha"], ref) < 1e-4
+    assert relerr(r0["pred"], fo.falkon_predict(Xv, X[idx], ref, "laplacian", 7.0)) < 1e-4
