@@ -149,6 +149,45 @@ def alignment_goldens():
     np.savez_compressed(os.path.join(GOLD, "alignment.npz"), **out)
 
 
+def consensus_goldens():
+    """
+    Pins oracle/consensus_oracle.py against the reference's own interpolated_features.py (imported by file
+    path): optimal interpolation times and interpolated projections on seeded principal-vector projections.
+    """
+    from oracle import consensus_oracle as co
+
+    spec = importlib.util.spec_from_file_location("ref_interp", "/root/reference/sobolev_alignment/interpolated_features.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.default_rng(7)
+    ns, nt, d = 700, 900, 4
+    shift = rng.normal(0, 1.0, size=d)
+    proj = {"source": {"source": rng.normal(0, 1, (ns, d)), "target": rng.normal(0, 1, (nt, d)) + 0.5 * shift},
+            "target": {"source": rng.normal(0, 1, (ns, d)) - 0.3 * shift, "target": rng.normal(0, 1.5, (nt, d))}}
+    for m in proj:
+        for k in proj[m]:
+            proj[m][k] = proj[m][k] - proj[m][k].mean(0, keepdims=True)
+    cosines = np.array([0.95, 0.8, 0.55, 0.2])
+    angles = np.arccos(cosines)
+    out = {"cosines": cosines}
+    for m in proj:
+        for k in proj[m]:
+            out[f"proj_{m}_{k}"] = proj[m][k]
+    taus = []
+    for pv in range(d):
+        t_ref = ref.compute_optimal_tau(pv, proj, angles, n_interpolation=100)
+        t_or = co.optimal_tau(pv, proj, angles)
+        s_ref, g_ref = ref.project_on_interpolate_PV(angles[pv], pv, t_ref, proj)
+        s_or, g_or = co.interpolate(angles[pv], pv, t_or, proj)
+        print(f"[consensus pin] PV {pv}: tau reference {t_ref:.2f} oracle {t_or:.2f}; "
+              f"max |interp diff| {max(np.abs(s_ref - s_or).max(), np.abs(g_ref - g_or).max()):.1e}")
+        assert abs(t_ref - t_or) < 1e-12 and np.abs(s_ref - s_or).max() < 1e-12 and np.abs(g_ref - g_or).max() < 1e-12
+        taus.append(t_ref)
+        out[f"interp_source_{pv}"], out[f"interp_target_{pv}"] = s_ref, g_ref
+    out["taus"] = np.array(taus)
+    np.savez_compressed(os.path.join(GOLD, "consensus.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -156,5 +195,6 @@ if __name__ == "__main__":
     krr_test_goldens()
     config1_goldens()
     alignment_goldens()
+    consensus_goldens()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))

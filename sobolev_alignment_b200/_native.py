@@ -179,6 +179,10 @@ class Prepared:
     def __init__(self, data, norms, n, p):
         self.data, self.norms, self.n, self.p, self.p_pad = data, norms, n, p, data.shape[1]
 
+    def head(self, m: int) -> "Prepared":
+        """View of the first m rows (the norm padding of the view is re-zeroed by the prep that fills it)."""
+        return Prepared(self.data[:m], self.norms[: round_up(max(m, 1), NORM_PAD)], m, self.p)
+
 
 def prep(X: torch.Tensor, shift: torch.Tensor | None, scale: torch.Tensor | None, gscale: float,
          out: Prepared | None = None, row_offset: int = 0) -> Prepared:

@@ -74,7 +74,8 @@ struct Job {
 struct Params {
   Job job[2];
   int njobs, nblk, dp, chunk, nitems;
-  int* sync;        // [0] ticket | [SYNC_HDR + (2 j) nblk + blk] published | [SYNC_HDR + (2 j + 1) nblk + row] partial count
+  int* sync;        // [0] ticket | per job j, [SYNC_HDR + (3 j + i) nblk + ..]: i = 0 converted x published (by block),
+                    // 1 partial-sum count (by chain row), 2 fp32 x written (by block)
   float* partial;   // [njobs][nblk][128 x 32]
   uint8_t* xhat;    // [njobs][nblk][xhat_bytes]
   long long* trace; // developer tool (option SAB_TRSM_TRACE_PTR): 8 globaltimer stamps per block of job 0
@@ -173,19 +174,20 @@ struct Smem {
   unsigned long long full[NSLOT], empty[NSLOT], xfull[NXSLOT], xempty[NXSLOT], iqfull[IQ], iqempty[IQ];
   Item iq[IQ];
   float red[2][NCONS];
+  float tscale[2][4];   // 1 / operand scale of {tiles, inverse blocks, W tiles} per job
 };
 
 // 128x128 (half: 64 stored rows) tile product on the legacy tensor path: acc += hi x_hi, acx += lo x_hi + hi x_lo.
 // `tile` = shared address of the half-tile slot, `lrow0` = first stored row (within the slot) of this k16 step /
 // row block, xop = shared address of the converted operand ([n][k] hi, then lo at +NP*256).
-template <int NB8, bool TRANS>
-__device__ __forceinline__ void mma_steps(uint32_t tile, uint32_t xop, int kstep0, int nsteps, int m0_or_lrow,
+template <int NB8, bool TRANS, int NSTEPS>
+__device__ __forceinline__ void mma_steps(uint32_t tile, uint32_t xop, int kstep0, int m0_or_lrow,
                                           float (&acc)[NB8][4], float (&acx)[NB8][4]) {
   constexpr int NP = NB8 * 8;
   const int lane = threadIdx.x & 31;
   const int j = lane >> 3, i = lane & 7;
 #pragma unroll
-  for (int s = 0; s < nsteps; ++s) {
+  for (int s = 0; s < NSTEPS; ++s) {
     const int ks = kstep0 + s;   // k16 step index within the 128-long contraction
     uint32_t ahi[4], alo[4];
     if (!TRANS) {
@@ -262,6 +264,10 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
     }
     fence_barrier_init();
   }
+  if (threadIdx.x < 8)
+    sm.tscale[threadIdx.x >> 2][threadIdx.x & 3] =
+        (static_cast<int>(threadIdx.x >> 2) < p.njobs && (threadIdx.x & 3) < 3)
+            ? __ldg(p.job[threadIdx.x >> 2].scales + (threadIdx.x & 3)) : 0.f;
   __syncthreads();
 
   auto blk_of = [&](int chain) { return TRANS ? nblk - 1 - chain : chain; };
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
       ++nq;
       if (it.c < 0) break;
       const int nt = ntiles_of(it);
-      const int* pub = p.sync + SYNC_HDR + (2 * it.job) * nblk;
+      const int* pub = p.sync + SYNC_HDR + (3 * it.job) * nblk;
       const uint8_t* xh = p.xhat + static_cast<long long>(it.job) * nblk * XB;
       for (int i = 0; i < nt; ++i, ++xg) {
         const int kd = kind_of(it, i);
@@ -409,8 +415,9 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
       const int blk = blk_of(it.c);
       const int nt = ntiles_of(it);
       const bool tr = p.trace != nullptr && it.fin && it.job == 0;
-      int* pub = p.sync + SYNC_HDR + (2 * it.job) * nblk;
-      int* pcnt = p.sync + SYNC_HDR + (2 * it.job + 1) * nblk;
+      int* pub = p.sync + SYNC_HDR + (3 * it.job) * nblk;
+      int* pcnt = p.sync + SYNC_HDR + (3 * it.job + 1) * nblk;
+      int* pub32 = p.sync + SYNC_HDR + (3 * it.job + 2) * nblk;
       float* part = p.partial + (static_cast<long long>(it.job) * nblk + it.c) * (TS * 32);
       const long long frow = static_cast<long long>(blk) * TS + m0 + g8;   // global row of fragment rows (+8)
       if (tr) stamp(blk, 7);
@@ -470,7 +477,7 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
         if (kd == KIND_INV) {
           // operand = b_c - (sum of all eliminated dependencies), converted by this CTA into the handed-over slot
           if (it.job == 1) {
-            wait_flag_ge(p.sync + SYNC_HDR + blk, 1, blk, 0u);   // job 0 has published this block
+            wait_flag_ge(p.sync + SYNC_HDR + 2 * nblk + blk, 1, blk, 0u);   // job 0 has written this block (fp32)
             load_rhs();
           }
           float v[NB8][4];
@@ -500,7 +507,7 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
           const int g = 2 * T + myhalf, s = g % NSLOT;
           mbar_wait(smem_u32(&sm.full[s]), (g / NSLOT) & 1);
           if (tr && kd == KIND_W) stamp(blk, 2);
-          mma_steps<NB8, false>(ring_a + s * HALF_BYTES, xop, 0, 8, m0 - myhalf * 64, acc, acx);
+          mma_steps<NB8, false, 8>(ring_a + s * HALF_BYTES, xop, 0, m0 - myhalf * 64, acc, acx);
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&sm.empty[s]));
         } else {
@@ -509,7 +516,7 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
             const int g = 2 * T + h, s = g % NSLOT;
             mbar_wait(smem_u32(&sm.full[s]), (g / NSLOT) & 1);
             if (tr && kd == KIND_W && h == 1) stamp(blk, 2);
-            mma_steps<NB8, true>(ring_a + s * HALF_BYTES, xop, h * 4, 4, m0, acc, acx);
+            mma_steps<NB8, true, 4>(ring_a + s * HALF_BYTES, xop, h * 4, m0, acc, acx);
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&sm.empty[s]));
           }
@@ -519,7 +526,7 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&sm.xempty[xs]));
         }
-        const float r = __ldg(J.scales + kd) * xinv;
+        const float r = sm.tscale[it.job][kd] * xinv;
 #pragma unroll
         for (int nb = 0; nb < NB8; ++nb)
 #pragma unroll
@@ -546,19 +553,14 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
           st_release_gpu(pcnt + it.c, it.q + 1);
         }
       } else {
-        // x_c: fp32 result + the converted operand every later block row will use
+        // x_c: the converted operand every later block row waits for goes out FIRST (it is the chain); the
+        // fp32 result (final output, and job 1's right-hand side) follows behind a flag of its own
         if (tr) stamp(blk, 3);
         float m = 0.f;
 #pragma unroll
-        for (int nb = 0; nb < NB8; ++nb) {
-          const int cc = nb * 8 + 2 * t4;
-          if (cc < dp) {
-            __stcg(reinterpret_cast<float2*>(J.x + frow * dp + cc), make_float2(U[nb][0], U[nb][1]));
-            __stcg(reinterpret_cast<float2*>(J.x + (frow + 8) * dp + cc), make_float2(U[nb][2], U[nb][3]));
-          }
+        for (int nb = 0; nb < NB8; ++nb)
 #pragma unroll
           for (int q = 0; q < 4; ++q) m = fmaxf(m, fabsf(U[nb][q]));
-        }
         float sc;
         const float inv = pick_scale(block_max(m), sc);   // (its barrier: every warp is done reading the slot)
         if (tr) stamp(blk, 4);
@@ -581,6 +583,21 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
           fence_proxy_async_all();
           st_release_gpu(pub + blk, 1);
           if (tr) stamp(blk, 6);
+        }
+#pragma unroll
+        for (int nb = 0; nb < NB8; ++nb) {
+          const int cc = nb * 8 + 2 * t4;
+          if (cc < dp) {
+            __stcg(reinterpret_cast<float2*>(J.x + frow * dp + cc), make_float2(U[nb][0], U[nb][1]));
+            __stcg(reinterpret_cast<float2*>(J.x + (frow + 8) * dp + cc), make_float2(U[nb][2], U[nb][3]));
+          }
+        }
+        if (p.njobs > 1 && it.job == 0) {
+          consumer_bar();
+          if (threadIdx.x == 0) {
+            __threadfence();
+            st_release_gpu(pub32 + blk, 1);
+          }
         }
       }
     }
@@ -798,7 +815,7 @@ extern "C" int sa_trsm_pack(void* stream, const float* L, int64_t M, int64_t ldl
 extern "C" int64_t sa_trsm_workspace_bytes(int64_t M) {
   if (M <= 0 || M % TS != 0) return -1;
   const int64_t nblk = M / TS;
-  int64_t b = (SYNC_HDR + 4 * nblk) * 4;
+  int64_t b = (SYNC_HDR + 6 * nblk) * 4;
   b = (b + 255) / 256 * 256;
   b += 2 * nblk * TS * 32 * 4;                 // partial sums
   b += 2 * nblk * ((xhat_bytes(4) + 127) / 128 * 128);   // converted x blocks
@@ -819,7 +836,7 @@ static int solve_jobs(cudaStream_t st, Params& p, int64_t M, int dp, int transpo
   p.nitems = static_cast<int>(count_items(p.njobs, nblk, p.chunk));
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   p.sync = reinterpret_cast<int*>(ws);
-  int64_t off = (SYNC_HDR + 4ll * nblk) * 4;
+  int64_t off = (SYNC_HDR + 6ll * nblk) * 4;
   off = (off + 255) / 256 * 256;
   p.partial = reinterpret_cast<float*>(ws + off);
   off += 2ll * nblk * TS * 32 * 4;
@@ -828,7 +845,7 @@ static int solve_jobs(cudaStream_t st, Params& p, int64_t M, int dp, int transpo
     char tp[64];
     p.trace = option("SAB_TRSM_TRACE_PTR", tp) ? reinterpret_cast<long long*>(std::strtoull(tp, nullptr, 0)) : nullptr;
   }
-  SAB_CHECK_CUDA(cudaMemsetAsync(p.sync, 0, (SYNC_HDR + 4ll * nblk) * 4, st));
+  SAB_CHECK_CUDA(cudaMemsetAsync(p.sync, 0, (SYNC_HDR + 6ll * nblk) * 4, st));
   switch ((dp + 7) / 8) {
     case 1: return launch_solve<1>(st, p, transpose);
     case 2: return launch_solve<2>(st, p, transpose);

@@ -12,6 +12,7 @@ stand-in defined under tests/ (never importable from here).
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -58,7 +59,7 @@ class CudaOps:
     name = "cuda"
     ltl_sharded = True     # L^T L can be formed in parts (sa_ltl_part) and summed over the ranks
 
-    def __init__(self, device=None, stage_rows: int = 65536):
+    def __init__(self, device=None, stage_rows: int = 65536, copy_threads: int | None = None):
         if not torch.cuda.is_available():
             raise nat.NativeLibraryError(
                 "sobolev_alignment_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
@@ -68,6 +69,8 @@ class CudaOps:
         self._pinned = None
         self._pinned_events = [None, None]   # last device-side use of each pinned staging buffer
         self._side = None
+        self._pool = None
+        self.copy_threads = max(1, min(8, (os.cpu_count() or 2) // 2)) if copy_threads is None else int(copy_threads)
 
     def staging_stream(self):
         """Side stream on which host inputs are copied / prepared while the main stream builds the preconditioner."""
@@ -111,13 +114,41 @@ class CudaOps:
         return Frame(shift, scale, gscale)
 
     # ------------------------------------------------------------------ operand preparation
-    def prepare(self, X: torch.Tensor, frame: Frame) -> nat.Prepared:
-        """Rows of X (CPU or CUDA, any float dtype) -> prepared fp16 operand resident on the device."""
+    def _host_copy(self, dst: torch.Tensor, src: torch.Tensor):
+        """
+        dst (pinned) <- src (pageable, possibly memmap-backed), split over a few threads: one thread moves
+        ~1-5 GB/s (page faults on a memmap), which would leave the H2D link idle (torch's copy releases the GIL).
+        """
+        n = src.shape[0]
+        T = self.copy_threads
+        if T <= 1 or n * src.shape[1] < (1 << 22):
+            dst.copy_(src)
+            return
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+
+            self._pool = ThreadPoolExecutor(max_workers=T, thread_name_prefix="sobolev-b200-copy")
+        step = (n + T - 1) // T
+        futs = [self._pool.submit(dst[a: a + step].copy_, src[a: a + step]) for a in range(0, n, step)]
+        for f in futs:
+            f.result()
+
+    def alloc_prepared(self, n: int, p: int) -> nat.Prepared:
+        return nat.alloc_prepared(n, p, self.device)
+
+    def prepare(self, X: torch.Tensor, frame: Frame, out: nat.Prepared | None = None) -> nat.Prepared:
+        """
+        Rows of X (CPU or CUDA, any float dtype) -> prepared fp16 operand resident on the device (`out`, when
+        given, must hold exactly X.shape[0] rows: the streaming callers reuse two buffers).
+        """
         n, p = X.shape
+        if out is not None and (out.n != n or out.p != p):
+            raise ValueError("prepared buffer does not match the rows to prepare")
         if X.is_cuda:
             Xd = X if X.dtype == torch.float32 and X.stride(1) == 1 else X.float().contiguous()
-            return nat.prep(Xd, frame.shift, frame.scale, frame.gscale)
-        out = nat.alloc_prepared(n, p, self.device)
+            return nat.prep(Xd, frame.shift, frame.scale, frame.gscale, out=out)
+        if out is None:
+            out = nat.alloc_prepared(n, p, self.device)
         if n == 0:
             return out
         rows = max(1, min(self.stage_rows, n))
@@ -141,13 +172,56 @@ class CudaOps:
             if src.is_pinned() and src.dtype == torch.float32 and src.is_contiguous():
                 dev_bufs[b][: e - s].copy_(src, non_blocking=True)
             else:
-                self._pinned[b][: e - s].copy_(src)  # never writes into the caller's (maybe memmap) data
+                self._host_copy(self._pinned[b][: e - s], src)  # never writes into the caller's (maybe memmap) data
                 dev_bufs[b][: e - s].copy_(self._pinned[b][: e - s], non_blocking=True)
             nat.prep(dev_bufs[b][: e - s], frame.shift, frame.scale, frame.gscale, out=out, row_offset=s)
             ev = torch.cuda.Event()
             ev.record(stream)
             events[b] = ev
         return out
+
+    def stream_rows(self, X: torch.Tensor, frame: Frame, fn, row_chunk: int = 131072):
+        """
+        fn(prepared_chunk, first_row) for consecutive row chunks of X.  Host rows are staged (pinned copy,
+        H2D, fp16 preparation) on the side stream one chunk AHEAD of the main stream's work on the previous
+        chunk, in two alternating buffers -- the caller's kernels and the copies overlap.
+        """
+        n, p = X.shape
+        if n == 0:
+            return
+        if X.is_cuda or n <= row_chunk:
+            for s in range(0, n, row_chunk):
+                fn(self.prepare(X[s: s + row_chunk], frame), s)
+            return
+        main = torch.cuda.current_stream(self.device)
+        side = self.staging_stream()
+        bufs = [nat.alloc_prepared(row_chunk, p, self.device) for _ in range(2)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        free = [None, None]
+        side.wait_stream(main)              # frame tensors were produced on the main stream
+
+        def stage(k):
+            b, s = k & 1, k * row_chunk
+            e = min(n, s + row_chunk)
+            view = bufs[b] if e - s == row_chunk else bufs[b].head(e - s)
+            with torch.cuda.stream(side):
+                if free[b] is not None:
+                    side.wait_event(free[b])
+                self.prepare(X[s:e], frame, out=view)
+                ready[b].record(side)
+            return view
+
+        nchunks = (n + row_chunk - 1) // row_chunk
+        nxt = stage(0)
+        for k in range(nchunks):
+            cur, b = nxt, k & 1
+            main.wait_event(ready[b])
+            fn(cur, k * row_chunk)
+            free[b] = torch.cuda.Event()
+            free[b].record(main)
+            if k + 1 < nchunks:
+                nxt = stage(k + 1)
+        main.wait_stream(side)
 
     # ------------------------------------------------------------------ numerical operations
     def kmv(self, spec: KernelSpec, frame: Frame, A, B, V, out, symmetric=False):

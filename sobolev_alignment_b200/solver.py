@@ -382,13 +382,25 @@ class Predictor:
             blk[:, : c1 - c0] = alpha_d[:, c0:c1]
             self.alpha_chunks.append((c0, c1, blk))
 
-    def predict(self, X: torch.Tensor, row_chunk: int = 262144) -> torch.Tensor:
+    def predict(self, X: torch.Tensor, row_chunk: int = 131072) -> torch.Tensor:
+        """K(X, C) alpha; host rows are staged one chunk ahead of the fused kernel (engine.stream_rows)."""
         ops = self.ops
         out = ops.zeros(X.shape[0], self.d)
-        for s in range(0, X.shape[0], row_chunk):
-            Xp = ops.prepare(X[s : s + row_chunk], self.frame)
+
+        def one_chunk(Xp, s):
             for c0, c1, blk in self.alpha_chunks:
                 part = ops.zeros(Xp.n, blk.shape[1])
                 ops.kmv(self.spec, self.frame, Xp, self.Cprep, blk, part)
-                out[s : s + row_chunk, c0:c1] = part[:, : c1 - c0]
+                out[s: s + Xp.n, c0:c1] = part[:, : c1 - c0]
+
+        stream_rows(ops, X, self.frame, one_chunk, row_chunk)
         return out
+
+
+def stream_rows(ops, X, frame, fn, row_chunk: int = 131072):
+    """fn(prepared_chunk, first_row) over row chunks of X, pipelined by the engine when it can."""
+    impl = getattr(ops, "stream_rows", None)
+    if impl is not None:
+        return impl(X, frame, fn, row_chunk)
+    for s in range(0, X.shape[0], row_chunk):
+        fn(ops.prepare(X[s: s + row_chunk], frame), s)

@@ -188,6 +188,81 @@ def test_alignment_golden(tag, kernel, params):
     assert relerr(gram(src.kernel_, Cs, a_s, Cs, a_s), g[f"{tag}_M_X"]) < 2e-4
 
 
+def test_consensus_projections_match_oracle():
+    """
+    compute_consensus_features' numeric core (sobolev_alignment.py:1027-1088): the four projections of
+    (source, target) data on (source, target) principal vectors -- each dataset prepared once, rotation folded
+    into the coefficient block, several streamed row chunks -- against the float64 restatement; then the
+    optimal interpolation times and interpolated features.
+    """
+    from oracle import consensus_oracle as co
+    from sobolev_alignment_b200 import consensus
+
+    g = load_golden("alignment")
+    n, p, d = 1500, 200, 8
+    Xs, Xt = syn.log_counts_numpy(n, p, seed=21), syn.log_counts_numpy(n, p, seed=22)
+    Ys, Yt = torch.from_numpy(syn.targets_numpy(Xs, d, seed=23)), torch.from_numpy(syn.targets_numpy(Xt, d, seed=23))
+    Xs, Xt = torch.from_numpy(Xs), torch.from_numpy(Xt)
+    krr = {"source": KRRApprox(method="falkon", kernel="laplacian", kernel_params={"sigma": 8.0}, penalization=1e-6, M=300),
+           "target": KRRApprox(method="falkon", kernel="laplacian", kernel_params={"sigma": 8.0}, penalization=1e-6, M=300)}
+    _fit_with_centres(krr["source"], Xs, Ys, g["idx_s"])
+    _fit_with_centres(krr["target"], Xt, Yt, g["idx_t"])
+    cmp_ = EncoderComparison(krr["source"], krr["target"]).compare().principal_vectors()
+    X = {"source": Xs, "target": Xt[:1100]}                     # different sample counts on the two sides
+    proj = consensus.pv_projections(krr, X, cmp_.principal_vectors_coef_, row_chunk=512)   # 3 chunks per dataset
+    ref = co.pv_projections({m: krr[m].sample_weights_ for m in krr}, {m: krr[m].anchors() for m in krr}, X,
+                            cmp_.principal_vectors_coef_, "laplacian", 8.0)
+    for m in ("source", "target"):
+        for k in ("source", "target"):
+            assert proj[m][k].shape == ref[m][k].shape
+            assert relerr(proj[m][k], ref[m][k]) < PRED_TOL, (m, k)
+            assert abs(proj[m][k].mean(0)).max() < 1e-5          # mean-centred (StandardScaler(with_std=False))
+    # the reference's route: four transforms, rotated on the host (sobolev_alignment.py:1027-1052)
+    rot = cmp_.untransformed_rotations_["source"].T.dot(cmp_.sqrt_inv_matrices_["source"])
+    via_transform = rot.dot(krr["source"].transform(X["target"]).numpy().astype(np.float64).T).T
+    via_transform -= via_transform.mean(0, keepdims=True)
+    assert relerr(proj["source"]["target"], via_transform) < PRED_TOL
+    feats, taus = consensus.consensus_features(krr, X, cmp_.principal_vectors_coef_, cmp_.principal_angles, 3, row_chunk=512)
+    assert feats.shape == (1500 + 1100, 3) and sorted(taus) == [0, 1, 2]
+    angles = np.arccos(np.clip(cmp_.principal_angles, -1, 1))
+    for k in range(3):
+        _, ks_ref = co.ks_curve(k, ref, angles)
+        assert ks_ref[int(round(taus[k] * 100))] <= ks_ref.min() + 5e-3      # (near-)optimal on the oracle's KS curve
+        s_ref, t_ref = co.interpolate(angles[k], k, taus[k], ref)
+        assert relerr(feats[:, k], np.concatenate([s_ref, t_ref])) < PRED_TOL
+
+
+@pytest.mark.parametrize("n_factors", [6, None])
+def test_null_model_matches_dense_oracle(n_factors):
+    """
+    null_model_similarity through `K c` products of the fused kernel (no M x M matrix) against the float64
+    restatement with dense kernel matrices, same torch seed (sobolev_alignment.py:1731-1810).  n_factors=None is
+    the reference's literal choice, anchors().shape[1].
+    """
+    from oracle import null_oracle
+    from sobolev_alignment_b200.null_model import null_model_similarity
+
+    n, p, d, M = 900, 40, 4, 260
+    Xs, Xt = syn.log_counts_numpy(n, p, seed=51), syn.log_counts_numpy(n, p, seed=52)
+    Ys, Yt = torch.from_numpy(syn.targets_numpy(Xs, d, seed=53)), torch.from_numpy(syn.targets_numpy(Xt, d, seed=53))
+    Xs, Xt = torch.from_numpy(Xs), torch.from_numpy(Xt)
+    src = KRRApprox(method="falkon", kernel="matern", kernel_params={"sigma": 5.0, "nu": 1.5}, penalization=1e-5, M=M)
+    tgt = KRRApprox(method="falkon", kernel="matern", kernel_params={"sigma": 5.0, "nu": 1.5}, penalization=1e-5, M=M)
+    _fit_with_centres(src, Xs, Ys, syn.centre_indices(n, M, seed=54))
+    _fit_with_centres(tgt, Xt, Yt, syn.centre_indices(n, M, seed=55))
+    cmp_ = EncoderComparison(src, tgt).compare()
+    torch.manual_seed(123)
+    got = null_model_similarity(src, tgt, cmp_.M_X, cmp_.M_Y, n_iter=35, return_all=True, n_factors=n_factors)
+    torch.manual_seed(123)
+    ref = null_oracle.null_model(src.anchors(), tgt.anchors(), cmp_.M_X.numpy(), cmp_.M_Y.numpy(), "matern", 5.0, 1.5,
+                                 n_iter=35, n_factors=n_factors)
+    assert got.shape == ref.shape == (35, 6 if n_factors else p)
+    assert np.abs(got - ref).max() < PRED_TOL               # singular values are cosines in [0, 1]
+    torch.manual_seed(123)
+    q = null_model_similarity(src, tgt, cmp_.M_X, cmp_.M_Y, n_iter=35, quantile=0.95, n_factors=n_factors)
+    assert abs(q - np.quantile(ref[:, 0], 0.95)) < PRED_TOL
+
+
 # ---------------------------------------------------------------------------- row-sharded fit on the real engine
 def _sharded_rank_main(rank, world, port, out_dir):
     import os

@@ -347,3 +347,77 @@ def test_row_sharded_fit_with_distributed_preconditioner_gloo(tmp_path):
     ref = fo.falkon_fit(X, Y, X[idx], "laplacian", 7.0, 1e-4)
     assert relerr(r0["alpha"], ref) < 1e-4
     assert relerr(r0["pred"], fo.falkon_predict(Xv, X[idx], ref, "laplacian", 7.0)) < 1e-4
+
+
+# ---------------------------------------------------------------------------- consensus features (host part)
+def test_interpolation_functions_match_reference_vectors():
+    """
+    sobolev_alignment_b200.consensus.compute_optimal_tau / project_on_interpolate_PV (batched torch KS statistics)
+    against the fixture generated by the reference's interpolated_features.py (oracle/make_golden.py).
+    """
+    from conftest import load_golden
+    from oracle import consensus_oracle as co
+    from sobolev_alignment_b200 import consensus
+
+    g = load_golden("consensus")
+    proj = {m: {k: g[f"proj_{m}_{k}"] for k in ("source", "target")} for m in ("source", "target")}
+    angles = np.arccos(g["cosines"])
+    for pv in range(len(angles)):
+        ks = consensus.ks_statistics(pv, proj, angles, device=torch.device("cpu"))
+        _, ks_ref = co.ks_curve(pv, proj, angles)
+        assert np.abs(ks - ks_ref).max() < 1e-12
+        tau = consensus.compute_optimal_tau(pv, proj, angles)
+        assert abs(tau - g["taus"][pv]) < 1e-12
+        s, t = consensus.project_on_interpolate_PV(angles[pv], pv, tau, proj)
+        assert np.abs(s - g[f"interp_source_{pv}"]).max() < 1e-12
+        assert np.abs(t - g[f"interp_target_{pv}"]).max() < 1e-12
+
+
+class _FakeKrr:
+    """The three things the alignment-side helpers read from a fitted KRRApprox."""
+
+    def __init__(self, kernel, anchors, weights):
+        self.kernel_, self._anchors, self.sample_weights_ = kernel, anchors, weights
+
+    def anchors(self):
+        return self._anchors
+
+
+def test_null_model_host_logic_on_stand_in_engine():
+    """Batched Gram-Schmidt through K c products == the literal dense restatement (same seed); CPU stand-in engine."""
+    from oracle import null_oracle
+    from sobolev_alignment_b200 import synthetic as syn
+    from sobolev_alignment_b200.null_model import null_model_similarity
+
+    A = torch.from_numpy(syn.log_counts_numpy(70, 9, seed=1))
+    B = torch.from_numpy(syn.log_counts_numpy(55, 9, seed=2))
+    k = MaternKernel(sigma=4.0, nu=1.5)
+    src, tgt = _FakeKrr(k, A, None), _FakeKrr(k, B, None)
+    M_X, M_Y = np.diag([2.0, 1.0, 0.5]), np.diag([1.5, 1.0, 0.7])
+    for nf in (3, None):
+        torch.manual_seed(5)
+        got = null_model_similarity(src, tgt, M_X, M_Y, n_iter=40, return_all=True, n_factors=nf, ops=CpuOps())
+        torch.manual_seed(5)
+        ref = null_oracle.null_model(A, B, M_X, M_Y, "matern", 4.0, 1.5, n_iter=40, n_factors=nf)
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() < 1e-9
+
+
+def test_consensus_projection_host_logic_on_stand_in_engine():
+    """pv_projections (shared frame, folded rotation, chunked rows) == the float64 restatement; CPU stand-in engine."""
+    from oracle import consensus_oracle as co
+    from sobolev_alignment_b200 import consensus, synthetic as syn
+
+    g = torch.Generator().manual_seed(3)
+    Cs, Ct = torch.from_numpy(syn.log_counts_numpy(40, 12, seed=1)), torch.from_numpy(syn.log_counts_numpy(50, 12, seed=2))
+    k = LaplacianKernel(sigma=5.0)
+    krr = {"source": _FakeKrr(k, Cs, torch.randn(40, 3, generator=g)),
+           "target": _FakeKrr(k, Ct, torch.randn(50, 3, generator=g))}
+    coef = {"source": torch.randn(3, 40, generator=g).numpy(), "target": torch.randn(3, 50, generator=g).numpy()}
+    X = {"source": torch.from_numpy(syn.log_counts_numpy(130, 12, seed=4)),
+         "target": torch.from_numpy(syn.log_counts_numpy(90, 12, seed=5))}
+    proj = consensus.pv_projections(krr, X, coef, row_chunk=50, ops=CpuOps())
+    ref = co.pv_projections(None, {m: krr[m].anchors() for m in krr}, X, coef, "laplacian", 5.0)
+    for m in proj:
+        for d in proj[m]:
+            assert relerr(proj[m][d], ref[m][d]) < 1e-5      # coefficients travel as float32

@@ -127,3 +127,23 @@ def test_preprocess_oracle_matches_sklearn_and_the_reference_lines():
             assert abs(orc.frob_norm_param - param) < 1e-12
     raw = PreprocessOracle(log_input=False, frob_norm_source=False).fit_transform("source", src)
     assert np.array_equal(raw, src)
+
+
+def _golden_projections():
+    g = load_golden("consensus")
+    proj = {m: {k: g[f"proj_{m}_{k}"] for k in ("source", "target")} for m in ("source", "target")}
+    return g, proj
+
+
+def test_consensus_oracle_matches_reference_interpolation():
+    """oracle/consensus_oracle.py against vectors produced by the reference's own interpolated_features.py."""
+    from oracle import consensus_oracle as co
+
+    g, proj = _golden_projections()
+    angles = np.arccos(g["cosines"])
+    for pv in range(len(angles)):
+        tau = co.optimal_tau(pv, proj, angles)
+        assert abs(tau - g["taus"][pv]) < 1e-12
+        s, t = co.interpolate(angles[pv], pv, tau, proj)
+        assert np.abs(s - g[f"interp_source_{pv}"]).max() < 1e-12
+        assert np.abs(t - g[f"interp_target_{pv}"]).max() < 1e-12
