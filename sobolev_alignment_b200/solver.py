@@ -75,28 +75,31 @@ class Preconditioner:
     Lower Cholesky factors L (= T^T) and LA (= A^T) of the Nystrom preconditioner, kept in the packed
     fp16 hi/lo tile form the triangular solves stream (`ops.trsm_pack`); the fp32 squares are released
     as soon as they are packed (the packed pair is half their size).
+
+    With several penalties (the model-selection grid, krr_model_selection.py:68-274) T -- which does not
+    depend on lambda -- is factored and packed once and G0 = T T^T / M is kept: per lambda only
+    A = chol(G0 + lambda I) is new (`LAp[k]`).
     """
 
-    def __init__(self, ops, spec: KernelSpec, frame, Cprep, penalty: float, pc_eps: float, comm=None,
-                 K: torch.Tensor | None = None):
+    def __init__(self, ops, spec: KernelSpec, frame, Cprep, penalties, pc_eps: float, comm=None):
         M = Cprep.n
         Mp = (M + TILE - 1) // TILE * TILE
         self.ops, self.M, self.Mp = ops, M, Mp
+        self.penalties = [float(x) for x in (penalties if isinstance(penalties, (list, tuple)) else [penalties])]
         nblk = Mp // TILE
         distributed = comm is not None and comm.enabled and comm.world > 1
-        if K is None:
-            # K_MM, padded with an identity block (leaves factors and solves of the leading block unchanged)
-            K = ops.zeros(Mp, Mp)
-            ops.kdense(spec, frame, Cprep, Cprep, K, symmetric=True)
-            if Mp > M:
-                K.diagonal()[M:] = 1.0
+        # K_MM, padded with an identity block (leaves factors and solves of the leading block unchanged)
+        K = ops.zeros(Mp, Mp)
+        ops.kdense(spec, frame, Cprep, Cprep, K, symmetric=True)
+        if Mp > M:
+            K.diagonal()[M:] = 1.0
         ops.add_diag(K, M, pc_eps * M)
         L_inv = ops.empty(nblk, TILE, TILE)
-        self.info = ops.zeros(2, dtype=torch.int32)
+        self.info = ops.zeros(1 + len(self.penalties), dtype=torch.int32)
         self._potrf(K, L_inv, self.info[0:1], comm if distributed else None)   # in place: K now holds L
         held = [K, L_inv]
         del K, L_inv        # `held` is the only reference: _finish releases the fp32 factor once it is packed
-        self._finish(held, penalty, comm if distributed else None)
+        self._finish(held, comm if distributed else None)
 
     def _potrf(self, A, inv, info, comm):
         if comm is not None and hasattr(self.ops, "potrf_panel"):
@@ -104,11 +107,13 @@ class Preconditioner:
         else:
             self.ops.potrf(A, inv, info)
 
-    def _finish(self, held, penalty, comm):
-        """From the factor L of K_MM + eps M I: G = L^T L / M + lambda I, its factor, and the packed forms."""
+    def _finish(self, held, comm):
+        """From the factor L of K_MM + eps M I: G = L^T L / M + lambda I, its factor(s), and the packed forms."""
         ops, M, Mp = self.ops, self.M, self.Mp
         L, L_inv = held
         nblk = Mp // TILE
+        lams = self.penalties
+        first = lams[0] if len(lams) == 1 else 0.0     # several penalties: keep G0 = L^T L / M without the ridge
         # A A^T ... : G = L^T L / M + lambda I  (= T T^T / M + lambda I), then its Cholesky factor
         if comm is not None and getattr(ops, "ltl_sharded", False):
             # L^T L has no sequential chain: every rank forms its share of the 512-row slabs and the
@@ -116,23 +121,32 @@ class Preconditioner:
             G = ops.zeros(Mp, Mp)
             ops.ltl(L, G, 1.0 / M, 0.0, comm.rank, comm.world)
             comm.all_reduce(G)
-            ops.add_diag(G, Mp, penalty)
+            if first != 0.0:
+                ops.add_diag(G, Mp, first)
         else:
             G = ops.empty(Mp, Mp)
-            ops.ltl(L, G, 1.0 / M, penalty)
+            ops.ltl(L, G, 1.0 / M, first)
         self.Lp = ops.trsm_pack(L, L_inv)
         held.clear()
         del L, L_inv
-        LA_inv = ops.empty(nblk, TILE, TILE)
-        self._potrf(G, LA_inv, self.info[1:2], comm)
-        self.LAp = ops.trsm_pack(G, LA_inv)
+        self.LAp = []
+        for k, lam in enumerate(lams):
+            last = k == len(lams) - 1
+            Gk = G if last else G.clone()               # the last factorisation may destroy G0
+            if len(lams) > 1:
+                ops.add_diag(Gk, Mp, lam)
+            LA_inv = ops.empty(nblk, TILE, TILE)
+            self._potrf(Gk, LA_inv, self.info[1 + k: 2 + k], comm)
+            self.LAp.append(ops.trsm_pack(Gk, LA_inv))
+            del Gk, LA_inv
 
     def check(self):
         info = self.ops.to_host(self.info).tolist()
-        if info[0] or info[1]:
-            which = "K_MM + eps*M*I" if info[0] else "T T^T / M + lambda*I"
+        if any(info):
+            bad = next(i for i, v in enumerate(info) if v)
+            which = "K_MM + eps*M*I" if bad == 0 else f"T T^T / M + lambda*I (lambda = {self.penalties[bad - 1]:g})"
             raise RuntimeError(
-                f"Cholesky of {which} failed at pivot {max(info) - 1}: matrix not positive definite "
+                f"Cholesky of {which} failed at pivot {info[bad] - 1}: matrix not positive definite "
                 "(increase penalization / check for duplicated centres)")
 
     # in-place solves on [Mp x dp] buffers
@@ -142,27 +156,44 @@ class Preconditioner:
     def invTt(self, v):
         return self.ops.trsm(self.Lp, v, False)
 
-    def invA(self, v):
-        return self.ops.trsm(self.LAp, v, True)
+    def invA(self, v, k=0):
+        return self.ops.trsm(self.LAp[k], v, True)
 
-    def invAt(self, v):
-        return self.ops.trsm(self.LAp, v, False)
+    def invAt(self, v, k=0):
+        return self.ops.trsm(self.LAp[k], v, False)
 
     # the operator always applies the factors in pairs: one launch with two interleaved chains
-    def invA_invT(self, v, z):
+    def invA_invT(self, v, z, k=0):
         """v <- A^-1 v (in place);  z <- T^-1 v."""
-        return self.ops.trsm_pair(self.LAp, self.Lp, v, z, None, 0.0, True)
+        return self.ops.trsm_pair(self.LAp[k], self.Lp, v, z, None, 0.0, True)
 
-    def invTt_invAt(self, w, out, v=None, lam=0.0):
+    def invTt_invAt(self, w, out, v=None, lam=0.0, k=0):
         """w <- T^-T w (in place);  out <- A^-T (w + lam v)."""
-        return self.ops.trsm_pair(self.Lp, self.LAp, w, out, v, lam, False)
+        return self.ops.trsm_pair(self.Lp, self.LAp[k], w, out, v, lam, False)
+
+
+class _CgColumns:
+    """CG state of one penalty: [Mp x dp] vectors, per-column scalars, device-side convergence scratch."""
+
+    def __init__(self, ops, B, maxiter):
+        Mp, dp = B.shape
+        self.B = B
+        self.X = ops.zeros(Mp, dp)
+        self.R = B.clone()
+        self.P = B.clone()
+        self.AP = ops.zeros(Mp, dp)
+        self.rs_old, self.rs_new, self.pAp = ops.empty(dp), ops.empty(dp), ops.empty(dp)
+        self.cgs = ops.cg_scratch(maxiter, dp)
+        self.v, self.z, self.w = ops.zeros(Mp, dp), ops.zeros(Mp, dp), ops.zeros(Mp, dp)
+        ops.coldot(self.R, self.R, self.rs_old, self.cgs)
 
 
 class FalkonSolver:
-    def __init__(self, ops, spec: KernelSpec, penalty: float, maxiter: int = 20, pc_eps: float = 1e-5,
+    def __init__(self, ops, spec: KernelSpec, penalty, maxiter: int = 20, pc_eps: float = 1e-5,
                  cg_eps: float = 1e-7, cg_tol: float = 1e-7, full_grad_every: int = 10, comm: Comm | None = None):
         self.ops, self.spec = ops, spec
-        self.penalty, self.maxiter = float(penalty), int(maxiter)
+        self.penalties = [float(x) for x in (penalty if isinstance(penalty, (list, tuple)) else [penalty])]
+        self.penalty, self.maxiter = self.penalties[0], int(maxiter)
         self.pc_eps, self.cg_eps, self.cg_tol = float(pc_eps), float(cg_eps), float(cg_tol)
         self.full_grad_every = int(full_grad_every)
         self.comm = comm or Comm()
@@ -172,33 +203,46 @@ class FalkonSolver:
         self.n_kmv_ = 0
 
     # ------------------------------------------------------------------ products with K_nM
-    def _knm_t_knm(self, z, out):
-        """out[:M] = sum over local rows of K_g^T (K_g z[:M]), all-reduced over ranks."""
+    def _knm_t_knm(self, Z, out):
+        """out[:M] = sum over local rows of K_g^T (K_g Z[:M]), all-reduced over ranks (any <= 32 columns)."""
         ops, M = self.ops, self.M
         self.t_buf.zero_()
-        ops.kmv(self.spec, self.frame, self.Xprep, self.Cprep, z[:M], self.t_buf)
+        ops.kmv(self.spec, self.frame, self.Xprep, self.Cprep, Z[:M], self.t_buf)
         out.zero_()
         ops.kmv(self.spec, self.frame, self.Cprep, self.Xprep, self.t_buf, out[:M])
         self.n_kmv_ += 2
         self.comm.all_reduce(out)
         return out
 
-    def _bhb(self, u, out):
-        """out = BHB u  (u is left untouched; w1/w2 are scratch)."""
-        ops, pre = self.ops, self.pre
-        v, z, w = self.w1, self.w2, self.w3
-        v.copy_(u)
-        pre.invA_invT(v, z)               # v = A^-1 u ; z = T^-1 v
-        self._knm_t_knm(z, w)             # w = K_nM^T K_nM z
-        ops.axpby(1.0 / self.n_total, w, 0.0, w)   # w /= n
-        pre.invTt_invAt(w, out, v, self.penalty)    # out = A^-T (T^-T w + lambda v)
-        return out
+    def _bhb(self, states, src, dst):
+        """
+        dst_k = BHB_k src_k for every penalty k of the group: one K_nM^T K_nM product for all of them --
+        the columns of the group ride side by side through the two fused-kernel launches.
+        """
+        ops, pre, M = self.ops, self.pre, self.M
+        dp = states[0][1].B.shape[1]
+        wide = len(states) > 1
+        for j, (k, st) in enumerate(states):
+            st.v.copy_(getattr(st, src))
+            pre.invA_invT(st.v, st.z, k)                      # v = A_k^-1 u ; z = T^-1 v
+            if wide:
+                self.Zw[:, j * dp: (j + 1) * dp] = st.z
+        if wide:
+            self._knm_t_knm(self.Zw, self.Ww)                 # W = K_nM^T K_nM [z_1 | z_2 | ...]
+        else:
+            self._knm_t_knm(states[0][1].z, states[0][1].w)
+        for j, (k, st) in enumerate(states):
+            if wide:
+                st.w.copy_(self.Ww[:, j * dp: (j + 1) * dp])
+            ops.axpby(1.0 / self.n_total, st.w, 0.0, st.w)    # w /= n
+            pre.invTt_invAt(st.w, getattr(st, dst), st.v, self.penalties[k], k)   # A_k^-T (T^-T w + lambda v)
 
     # ------------------------------------------------------------------ fit
     def fit(self, X, Y, centres, n_total: int | None = None):
         """
         X [n x p], Y [n x d]: this rank's rows (CPU or CUDA).  centres [M x p]: identical on all ranks.
-        Returns alpha [M x d] (float32, on the engine's device).
+        Returns alpha [M x d] (float32, on the engine's device) -- a list of them, one per penalty, when the
+        solver was given a list of penalties.
         """
         ops = self.ops
         t0 = time.perf_counter()
@@ -236,8 +280,7 @@ class FalkonSolver:
 
             helper = threading.Thread(target=_stage, name="sobolev-b200-staging")
             helper.start()
-        self.pre = pre = Preconditioner(ops, self.spec, self.frame, self.Cprep, self.penalty, self.pc_eps, self.comm)
-        Mp = pre.Mp
+        self.pre = pre = Preconditioner(ops, self.spec, self.frame, self.Cprep, self.penalties, self.pc_eps, self.comm)
         if overlap:
             ev[1].record(main)
             helper.join()
@@ -260,23 +303,9 @@ class FalkonSolver:
         t2 = time.perf_counter()
         if overlap:
             ev[4].record(main)
-        # the right-hand sides are solved simultaneously, at most MAX_COLS columns per CG run (the fused
-        # kernel carries up to 32 columns of V); preconditioner and prepared rows are shared by the runs
         pre.check()
-        out = ops.zeros(M, d)
-        all_res, n_iter = [], 0
-        for c0 in range(0, d, MAX_COLS):
-            c1 = min(d, c0 + MAX_COLS)
-            dp = pad_cols(c1 - c0)
-            Yd = ops.zeros(n, dp)
-            Yd[:, : c1 - c0] = Yfull[:, c0:c1]
-            alpha = self._solve_columns(Yd, Mp, dp)
-            out[:, c0:c1] = alpha[:M, : c1 - c0]
-            all_res.append(list(self.residuals))
-            n_iter = max(n_iter, self.n_iter_)
+        outs = self.solve_prepared(Yfull)
         del Yfull
-        self.n_iter_ = n_iter
-        self.residuals = [max(r[i] for r in all_res if i < len(r)) for i in range(max(len(r) for r in all_res))]
         if overlap:
             self._phase_events[5].record(main)
         ops.synchronize()
@@ -290,77 +319,121 @@ class FalkonSolver:
         else:
             self.times["cg"] = time.perf_counter() - t2
         self.times["fit"] = time.perf_counter() - t0
-        return out
+        return outs if len(self.penalties) > 1 else outs[0]
 
-    def _solve_columns(self, Yd, Mp, dp):
-        """FALKON solve for the (padded) columns Yd [n x dp]; returns alpha [Mp x dp] (a scratch buffer)."""
-        ops, pre, M = self.ops, self.pre, self.M
-        n = Yd.shape[0]
-        self.t_buf = ops.empty(n, dp)
-        self.w1, self.w2, self.w3 = ops.zeros(Mp, dp), ops.zeros(Mp, dp), ops.zeros(Mp, dp)
-        B = ops.zeros(Mp, dp)
-        Bw = self.w3
-        # rhs = A^-T T^-T K_nM^T (Y / n)
-        ops.axpby(1.0 / self.n_total, Yd, 0.0, Yd)     # Y / n
-        Bw.zero_()
-        ops.kmv(self.spec, self.frame, self.Cprep, self.Xprep, Yd, Bw[:M])
-        self.n_kmv_ += 1
-        self.comm.all_reduce(Bw)
-        pre.invTt_invAt(Bw, B)            # B = A^-T T^-T K_nM^T (Y / n)
-        beta = self._conjugate_gradient(B, Mp, dp)
-        alpha = self.w2
-        pre.invA_invT(beta, alpha)        # alpha = T^-1 A^-1 beta
-        return alpha
-
-    def _conjugate_gradient(self, B, Mp, dp):
+    def solve_prepared(self, Yfull):
         """
-        Batched-column CG (falkon `ConjugateGradient.solve`).  Convergence is decided by the kernels (a
-        device flag freezes X once max_c sqrt(r_c^T r_c) < cg_tol); the host reads that flag LAG
-        iterations late, so no iteration ends in a device synchronisation, and -- the flag being a
-        function of bit-identical replicated state -- every rank leaves the loop at the same iteration.
+        FALKON solves for every penalty with self.pre / self.Xprep / self.Cprep / self.frame in place.  The
+        right-hand sides are solved simultaneously, at most MAX_COLS columns per fused-kernel launch: d > 32
+        runs in column chunks, and as many penalties as fit share a launch (32 // dp of them).
+        """
+        ops, pre, M = self.ops, self.pre, self.M
+        n, d = Yfull.shape
+        Mp = pre.Mp
+        nl = len(self.penalties)
+        outs = [ops.zeros(M, d) for _ in range(nl)]
+        traces = [[] for _ in range(nl)]
+        for c0 in range(0, d, MAX_COLS):
+            c1 = min(d, c0 + MAX_COLS)
+            dp = pad_cols(c1 - c0)
+            Yd = ops.zeros(n, dp)
+            Yd[:, : c1 - c0] = Yfull[:, c0:c1]
+            # T^-T K_nM^T (Y / n) does not depend on the penalty
+            ops.axpby(1.0 / self.n_total, Yd, 0.0, Yd)
+            tz = ops.zeros(Mp, dp)
+            ops.kmv(self.spec, self.frame, self.Cprep, self.Xprep, Yd, tz[:M])
+            self.n_kmv_ += 1
+            self.comm.all_reduce(tz)
+            del Yd
+            group = max(1, MAX_COLS // dp)
+            tzt = None
+            if nl > 1:                       # T^-T of it is shared by all penalties too
+                tzt = tz
+                pre.invTt(tzt)
+            for g0 in range(0, nl, group):
+                ks = list(range(g0, min(nl, g0 + group)))
+                self.t_buf = ops.empty(n, len(ks) * dp)
+                alphas = self._solve_group(tz, tzt, ks, Mp, dp)
+                for k, alpha in zip(ks, alphas):
+                    outs[k][:, c0:c1] = alpha[:M, : c1 - c0]
+                    traces[k].append(list(self._group_residuals[k]))
+        self.residuals_per_penalty = [
+            [max(r[i] for r in tr if i < len(r)) for i in range(max(len(r) for r in tr))] for tr in traces]
+        self.residuals = self.residuals_per_penalty[0]
+        self.n_iter_ = max(len(r) for r in self.residuals_per_penalty)
+        return outs
+
+    def _solve_group(self, tz, tzt, ks, Mp, dp):
+        """FALKON solve for the penalties `ks` (sharing the fused-kernel launches); returns [alpha_k] scratch buffers."""
+        ops, pre = self.ops, self.pre
+        if len(ks) > 1:
+            self.Zw, self.Ww = ops.zeros(Mp, len(ks) * dp), ops.zeros(Mp, len(ks) * dp)
+        states = []
+        for k in ks:
+            # B_k = A_k^-T T^-T K_nM^T (Y / n)
+            B = ops.zeros(Mp, dp)
+            if tzt is not None:
+                B.copy_(tzt)
+                pre.invAt(B, k)
+            else:
+                pre.invTt_invAt(tz, B, None, 0.0, k)
+            states.append((k, _CgColumns(ops, B, self.maxiter)))
+        self._conjugate_gradient(states)
+        alphas = []
+        self._group_residuals = {}
+        for k, st in states:
+            pre.invA_invT(st.X, st.z, k)          # alpha = T^-1 A_k^-1 beta
+            alphas.append(st.z)
+            hist = st.cgs.history()[: self._cg_done].double().clamp_min(0).max(dim=1).values.sqrt().tolist()
+            res = []
+            for r in hist:
+                res.append(r)
+                if r < self.cg_tol:
+                    break
+            self._group_residuals[k] = res
+        return alphas
+
+    def _conjugate_gradient(self, states):
+        """
+        Batched-column CG (falkon `ConjugateGradient.solve`) for a group of penalties in lock-step.
+        Convergence is decided by the kernels (a device flag per penalty freezes its X once
+        max_c sqrt(r_c^T r_c) < cg_tol); the host reads the flags LAG iterations late, so no iteration ends
+        in a device synchronisation, and -- the flags being functions of bit-identical replicated state --
+        every rank leaves the loop at the same iteration.
         """
         ops = self.ops
         LAG = 2
-        X = ops.zeros(Mp, dp)
-        R = B.clone()
-        P = B.clone()
-        AP = ops.zeros(Mp, dp)
-        rs_old, rs_new, pAp = ops.empty(dp), ops.empty(dp), ops.empty(dp)
-        cgs = ops.cg_scratch(self.maxiter, dp)
-        ops.coldot(R, R, rs_old, cgs)
         done = 0
         for it in range(self.maxiter):
-            if it >= LAG and cgs.stopped_at(it - LAG):
+            if it >= LAG and all(st.cgs.stopped_at(it - LAG) for _, st in states):
                 break
-            self._bhb(P, AP)
-            ops.coldot(P, AP, pAp, cgs)
+            self._bhb(states, "P", "AP")
             # Falkon recomputes the residual from scratch every `full_grad_every` iterations.  On the very
             # last iteration that product pair would only feed the reported residual (X is final), so
             # the recurrence is used there instead: same alpha, two fused-kernel launches fewer.
-            if (it + 1) % self.full_grad_every == 0 and it + 1 < self.maxiter:
-                ops.cg_update(P, None, X, None, rs_old, pAp, self.cg_eps, None, cgs)   # X += alpha P
-                self._bhb(X, R)                                                       # R = B - BHB X
-                ops.axpby(1.0, B, -1.0, R)
-                ops.coldot(R, R, rs_new, cgs, hist_row=it, tol=self.cg_tol)
-            else:
-                ops.cg_update(P, AP, X, R, rs_old, pAp, self.cg_eps, rs_new, cgs, hist_row=it, tol=self.cg_tol)
-            cgs.poll(it)
+            full = (it + 1) % self.full_grad_every == 0 and it + 1 < self.maxiter
+            for _, st in states:
+                ops.coldot(st.P, st.AP, st.pAp, st.cgs)
+                if full:
+                    ops.cg_update(st.P, None, st.X, None, st.rs_old, st.pAp, self.cg_eps, None, st.cgs)   # X += alpha P
+                else:
+                    ops.cg_update(st.P, st.AP, st.X, st.R, st.rs_old, st.pAp, self.cg_eps, st.rs_new, st.cgs,
+                                  hist_row=it, tol=self.cg_tol)
+            if full:
+                self._bhb(states, "X", "R")                                    # R = B - BHB X
+                for _, st in states:
+                    ops.axpby(1.0, st.B, -1.0, st.R)
+                    ops.coldot(st.R, st.R, st.rs_new, st.cgs, hist_row=it, tol=self.cg_tol)
             done = it + 1
-            ops.cg_direction(R, P, rs_new, rs_old, self.cg_eps, cgs)
-            rs_old, rs_new = rs_new, rs_old
-        # one read of the residual history; iterations after the first converged one were no-ops
-        hist = cgs.history()[:done].double().clamp_min(0).max(dim=1).values.sqrt().tolist()
-        self.residuals = []
-        for r in hist:
-            self.residuals.append(r)
-            if r < self.cg_tol:
-                break
-        self.n_iter_ = len(self.residuals)
-        return X
+            for _, st in states:
+                st.cgs.poll(it)
+                ops.cg_direction(st.R, st.P, st.rs_new, st.rs_old, self.cg_eps, st.cgs)
+                st.rs_old, st.rs_new = st.rs_new, st.rs_old
+        self._cg_done = done
 
     # ------------------------------------------------------------------ release
     def release(self):
-        for name in ("pre", "Xprep", "t_buf", "w1", "w2", "w3"):
+        for name in ("pre", "Xprep", "t_buf", "Zw", "Ww"):
             if hasattr(self, name):
                 delattr(self, name)
 

@@ -263,6 +263,22 @@ def test_null_model_matches_dense_oracle(n_factors):
     assert abs(q - np.quantile(ref[:, 0], 0.95)) < PRED_TOL
 
 
+def test_grid_matches_independent_fits():
+    """KRRGrid (shared operands, T per kernel, A per penalty, multi-lambda CG) against the oracle, point by point."""
+    from sobolev_alignment_b200.model_selection import KRRGrid
+
+    X, Xv, W, Y, Yv = krr_test_data(seed=14, n=3000, p=60, d=5, n_valid=64)
+    grid = KRRGrid(X, Y, M=500, sigma=float(np.sqrt(120)), kernel="matern", center_seed=7)
+    lams = [1e-8, 1e-5, 1e-3, 1e-1, 10.0]
+    out = grid.fit(nus=(0.5, 1.5, np.inf), penalizations=lams)
+    assert len(out) == 15
+    C = X[grid.centre_idx]
+    for (nu, lam), clf in out.items():
+        ref = fo.falkon_fit(X, Y, C, "matern", float(np.sqrt(120)), lam, nu=nu)
+        pred_ref = fo.falkon_predict(Xv, C, ref, "matern", float(np.sqrt(120)), nu)
+        assert relerr(clf.transform(Xv), pred_ref) < PRED_TOL, (nu, lam)
+
+
 # ---------------------------------------------------------------------------- row-sharded fit on the real engine
 def _sharded_rank_main(rank, world, port, out_dir):
     import os

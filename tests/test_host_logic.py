@@ -421,3 +421,34 @@ def test_consensus_projection_host_logic_on_stand_in_engine():
     for m in proj:
         for d in proj[m]:
             assert relerr(proj[m][d], ref[m][d]) < 1e-5      # coefficients travel as float32
+
+
+def test_grid_shares_preconditioner_and_cg_launches_stand_in_engine():
+    """
+    KRRGrid: per kernel one T, per penalty one A, CG of several penalties in lock-step through shared K_nM
+    products -- every grid point equals the independent float64 oracle fit with the same centres.
+    """
+    from sobolev_alignment_b200.model_selection import KRRGrid
+
+    X, Xv, W, Y, Yv = krr_test_data(seed=12, n=420, p=10, d=3, n_valid=20)
+    ops = CpuOps()
+    calls = {"kmv": 0}
+    orig = ops.kmv
+
+    def counting_kmv(*a, **k):
+        calls["kmv"] += 1
+        return orig(*a, **k)
+
+    ops.kmv = counting_kmv
+    grid = KRRGrid(X, Y, M=64, sigma=4.0, kernel="matern", center_seed=3, ops=ops)
+    lams = [1e-6, 1e-4, 1e-2, 1.0, 10.0]
+    out = grid.fit(nus=(0.5, 2.5), penalizations=lams)
+    assert len(out) == 10
+    # 2 kernels x (1 rhs product + 21 product pairs of ONE group of 5 penalties): not 10 x 43
+    assert calls["kmv"] == 2 * (1 + 2 * 21)
+    C = X[grid.centre_idx]
+    for (nu, lam), clf in out.items():
+        ref = fo.falkon_fit(X, Y, C, "matern", 4.0, lam, nu=nu)
+        assert relerr(clf.sample_weights_, ref) < 1e-6, (nu, lam)
+        assert clf.penalization == lam and clf.kernel_params["nu"] == nu
+        assert torch.equal(clf.anchors(), C)
