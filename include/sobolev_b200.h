@@ -61,6 +61,12 @@ int sa_device_info(int* sm_count, int* smem_bytes);
 int sa_prep(void* stream, const float* X, int64_t n, int64_t p, int64_t ldx, const float* shift,
             const float* scale, float gscale, void* out_f16, int64_t ldo, float* norms,
             int64_t norms_len);
+/* Same with f(x) = log10(x + 1) applied to X first (raw counts in): the reference's preprocessing chain
+ * (sobolev_alignment.py:851-902: log10(x + 1), StandardScaler, Frobenius gain) is affine after the log, so the
+ * caller folds it into shift / scale and no fp32 intermediate is ever written. */
+int sa_prep_log(void* stream, const float* X, int64_t n, int64_t p, int64_t ldx, const float* shift,
+                const float* scale, float gscale, void* out_f16, int64_t ldo, float* norms,
+                int64_t norms_len);
 
 /*
  * Input preprocessing of the artificial samples before the fit (SobolevAlignment._memmap_log_processing
@@ -71,7 +77,7 @@ int sa_prep(void* stream, const float* X, int64_t n, int64_t p, int64_t ldx, con
  * first row) so that the variance sumsq/n - (sum/n)^2 does not cancel; float64 accumulators, ACCUMULATED INTO
  * (the caller zeroes them; at most 65535 * 4096 rows per call).
  * sa_transform_rows: out[i, j] = (f(X[i, j]) - shift[j]) * scale[j] * gain (shift / scale may be NULL; out may
- * alias X); rownorm_sum (may be NULL) += sum_i |out[i, :]|_2, the numerator of the mean row norm of the
+ * alias X, or be NULL when only the row-norm sum is wanted); rownorm_sum (may be NULL) += sum_i |out[i, :]|_2, the numerator of the mean row norm of the
  * Frobenius normalisation.
  */
 int sa_colstats(void* stream, const float* X, int64_t n, int64_t p, int64_t ldx, int log10p1,

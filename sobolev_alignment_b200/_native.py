@@ -68,6 +68,8 @@ _SIGNATURES = {
     "sa_device_info": (c_int, [c_void_p, c_void_p]),
     "sa_prep": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_float,
                         c_void_p, c_int64, c_void_p, c_int64]),
+    "sa_prep_log": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_float,
+                            c_void_p, c_int64, c_void_p, c_int64]),
     "sa_colstats": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "sa_transform_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_float,
                                   c_void_p, c_int64, c_void_p]),
@@ -185,8 +187,8 @@ class Prepared:
 
 
 def prep(X: torch.Tensor, shift: torch.Tensor | None, scale: torch.Tensor | None, gscale: float,
-         out: Prepared | None = None, row_offset: int = 0) -> Prepared:
-    """sa_prep on a [n x p] fp32 CUDA tensor (row stride may exceed p)."""
+         out: Prepared | None = None, row_offset: int = 0, log10p1: bool = False) -> Prepared:
+    """sa_prep (sa_prep_log when `log10p1`: raw counts in) on a [n x p] fp32 CUDA tensor (row stride may exceed p)."""
     lib = load()
     if not X.is_cuda or X.dtype != torch.float32 or X.dim() != 2 or X.stride(1) != 1:
         raise NativeLibraryError("prep expects a 2-D float32 CUDA tensor with unit column stride")
@@ -206,7 +208,7 @@ def prep(X: torch.Tensor, shift: torch.Tensor | None, scale: torch.Tensor | None
         norms_len = (out.norms.numel() - row_offset) if last else n
     if n == 0:
         return out
-    _call(lib.sa_prep, X.device, X.data_ptr(), n, p, X.stride(0), _ptr(shift), _ptr(scale),
+    _call(lib.sa_prep_log if log10p1 else lib.sa_prep, X.device, X.data_ptr(), n, p, X.stride(0), _ptr(shift), _ptr(scale),
                        float(gscale), dptr, out.p_pad, nptr, norms_len)
     STATS.launches += 1
     return out
@@ -236,8 +238,11 @@ def colstats(X: torch.Tensor, log10p1: bool):
 
 
 def transform_rows(X: torch.Tensor, log10p1: bool, shift: torch.Tensor | None, scale: torch.Tensor | None,
-                   gain: float = 1.0, want_row_norms: bool = False):
-    """In place X <- (f(X) - shift) * scale * gain; returns sum_i |X_i|_2 (float64 scalar tensor) if asked."""
+                   gain: float = 1.0, want_row_norms: bool = False, in_place: bool = True):
+    """
+    X <- (f(X) - shift) * scale * gain in place; returns sum_i |row_i|_2 of the result (float64 scalar tensor)
+    if asked.  in_place=False: X is left untouched and only the row-norm sum is computed.
+    """
     lib = load()
     if not X.is_cuda or X.dtype != torch.float32 or X.dim() != 2 or X.stride(1) != 1:
         raise NativeLibraryError("transform_rows expects a 2-D float32 CUDA tensor with unit column stride")
@@ -245,7 +250,7 @@ def transform_rows(X: torch.Tensor, log10p1: bool, shift: torch.Tensor | None, s
     acc = torch.zeros(1, dtype=torch.float64, device=X.device) if want_row_norms else None
     if n:
         _call(lib.sa_transform_rows, X.device, X.data_ptr(), n, p, X.stride(0), int(log10p1), _ptr(shift), _ptr(scale),
-                                     float(gain), X.data_ptr(), X.stride(0), _ptr(acc))
+              float(gain), X.data_ptr() if in_place else None, X.stride(0), _ptr(acc))
         STATS.launches += 1
     return acc
 

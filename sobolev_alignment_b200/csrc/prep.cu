@@ -14,7 +14,13 @@ namespace sab {
 
 constexpr int PREP_WARPS = 8;
 
-template <bool VEC>
+// LOG: the rows are raw counts and f(x) = log10(x + 1) is applied first -- the reference's preprocessing chain
+// (log10(x + 1), StandardScaler, Frobenius gain: sobolev_alignment.py:851-902) is affine after the log, so it
+// folds into shift / scale and the fp32 intermediate is never written.
+template <bool LOG>
+__device__ __forceinline__ float pre_fn(float x) { return LOG ? log10f(x + 1.0f) : x; }
+
+template <bool VEC, bool LOG>
 __global__ void __launch_bounds__(PREP_WARPS * 32)
 prep_kernel(const float* __restrict__ X, long long n, int p, long long ldx,
             const float* __restrict__ shift, const float* __restrict__ scale, float gscale,
@@ -37,10 +43,10 @@ prep_kernel(const float* __restrict__ X, long long n, int p, long long ldx,
         float4 sh = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f);
         if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift) + q);
         if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale) + q);
-        const __half h0 = __float2half_rn((v.x - sh.x) * sc.x * gscale);
-        const __half h1 = __float2half_rn((v.y - sh.y) * sc.y * gscale);
-        const __half h2 = __float2half_rn((v.z - sh.z) * sc.z * gscale);
-        const __half h3 = __float2half_rn((v.w - sh.w) * sc.w * gscale);
+        const __half h0 = __float2half_rn((pre_fn<LOG>(v.x) - sh.x) * sc.x * gscale);
+        const __half h1 = __float2half_rn((pre_fn<LOG>(v.y) - sh.y) * sc.y * gscale);
+        const __half h2 = __float2half_rn((pre_fn<LOG>(v.z) - sh.z) * sc.z * gscale);
+        const __half h3 = __float2half_rn((pre_fn<LOG>(v.w) - sh.w) * sc.w * gscale);
         const float f0 = __half2float(h0), f1 = __half2float(h1), f2 = __half2float(h2),
                     f3 = __half2float(h3);
         acc = fmaf(f0, f0, acc);
@@ -56,7 +62,7 @@ prep_kernel(const float* __restrict__ X, long long n, int p, long long ldx,
       for (int j = (p4 << 2) + lane; j < p; j += 32) {
         const float sh = shift ? __ldg(shift + j) : 0.f;
         const float sc = scale ? __ldg(scale + j) : 1.f;
-        const __half h = __float2half_rn((x[j] - sh) * sc * gscale);
+        const __half h = __float2half_rn((pre_fn<LOG>(x[j]) - sh) * sc * gscale);
         const float f = __half2float(h);
         acc = fmaf(f, f, acc);
         o[j] = h;
@@ -65,7 +71,7 @@ prep_kernel(const float* __restrict__ X, long long n, int p, long long ldx,
       for (int j = lane; j < p; j += 32) {
         const float sh = shift ? __ldg(shift + j) : 0.f;
         const float sc = scale ? __ldg(scale + j) : 1.f;
-        const __half h = __float2half_rn((x[j] - sh) * sc * gscale);
+        const __half h = __float2half_rn((pre_fn<LOG>(x[j]) - sh) * sc * gscale);
         const float f = __half2float(h);
         acc = fmaf(f, f, acc);
         o[j] = h;
@@ -80,10 +86,10 @@ prep_kernel(const float* __restrict__ X, long long n, int p, long long ldx,
 
 }  // namespace sab
 
-extern "C" int sa_prep(void* stream, const float* X, int64_t n, int64_t p, int64_t ldx,
-                       const float* shift, const float* scale, float gscale, void* out_f16,
-                       int64_t ldo, float* norms, int64_t norms_len) {
-  using namespace sab;
+namespace sab {
+static int prep_launch(void* stream, const float* X, int64_t n, int64_t p, int64_t ldx, const float* shift,
+                       const float* scale, float gscale, void* out_f16, int64_t ldo, float* norms, int64_t norms_len,
+                       bool log10p1) {
   SAB_REQUIRE(n >= 0 && p > 0 && p < (1ll << 30), "bad shape n=%lld p=%lld", (long long)n, (long long)p);
   SAB_REQUIRE(ldx >= p && ldo >= p && ldo % 64 == 0, "need ldx >= p, ldo >= p and ldo %% 64 == 0 (ldx=%lld ldo=%lld)",
               (long long)ldx, (long long)ldo);
@@ -100,14 +106,27 @@ extern "C" int sa_prep(void* stream, const float* X, int64_t n, int64_t p, int64
   const long long max_blocks = static_cast<long long>(sms) * 8;
   if (blocks > max_blocks) blocks = max_blocks;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (vec)
-    prep_kernel<true><<<static_cast<int>(blocks), PREP_WARPS * 32, 0, st>>>(
-        X, n, static_cast<int>(p), ldx, shift, scale, gscale, static_cast<__half*>(out_f16), ldo, norms,
-        norms_len);
-  else
-    prep_kernel<false><<<static_cast<int>(blocks), PREP_WARPS * 32, 0, st>>>(
-        X, n, static_cast<int>(p), ldx, shift, scale, gscale, static_cast<__half*>(out_f16), ldo, norms,
-        norms_len);
+  auto go = [&](auto kern) {
+    kern<<<static_cast<int>(blocks), PREP_WARPS * 32, 0, st>>>(X, n, static_cast<int>(p), ldx, shift, scale, gscale,
+                                                               static_cast<__half*>(out_f16), ldo, norms, norms_len);
+  };
+  if (vec && log10p1) go(prep_kernel<true, true>);
+  else if (vec) go(prep_kernel<true, false>);
+  else if (log10p1) go(prep_kernel<false, true>);
+  else go(prep_kernel<false, false>);
   SAB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+}  // namespace sab
+
+extern "C" int sa_prep(void* stream, const float* X, int64_t n, int64_t p, int64_t ldx,
+                       const float* shift, const float* scale, float gscale, void* out_f16,
+                       int64_t ldo, float* norms, int64_t norms_len) {
+  return sab::prep_launch(stream, X, n, p, ldx, shift, scale, gscale, out_f16, ldo, norms, norms_len, false);
+}
+
+extern "C" int sa_prep_log(void* stream, const float* X, int64_t n, int64_t p, int64_t ldx,
+                           const float* shift, const float* scale, float gscale, void* out_f16,
+                           int64_t ldo, float* norms, int64_t norms_len) {
+  return sab::prep_launch(stream, X, n, p, ldx, shift, scale, gscale, out_f16, ldo, norms, norms_len, true);
 }

@@ -126,7 +126,7 @@ transform_rows_kernel(const float* __restrict__ X, long long n, int p, long long
         y.z = (fwd(v.z, log10p1) - sh.z) * sc.z * gain;
         y.w = (fwd(v.w, log10p1) - sh.w) * sc.w * gain;
         acc = fmaf(y.x, y.x, fmaf(y.y, y.y, fmaf(y.z, y.z, fmaf(y.w, y.w, acc))));
-        reinterpret_cast<float4*>(o)[q] = y;
+        if (out != nullptr) reinterpret_cast<float4*>(o)[q] = y;
       }
       j0 = p4 << 2;
     }
@@ -135,7 +135,7 @@ transform_rows_kernel(const float* __restrict__ X, long long n, int p, long long
       const float sc = scale ? __ldg(scale + j) : 1.f;
       const float y = (fwd(x[j], log10p1) - sh) * sc * gain;
       acc = fmaf(y, y, acc);
-      o[j] = y;
+      if (out != nullptr) o[j] = y;
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
@@ -172,9 +172,9 @@ extern "C" int sa_transform_rows(void* stream, const float* X, int64_t n, int64_
                                  const float* shift, const float* scale, float gain, float* out, int64_t ldo,
                                  double* rownorm_sum) {
   using namespace sab;
-  SAB_REQUIRE(n >= 0 && p > 0 && p < (1ll << 30) && ldx >= p && ldo >= p, "bad shape n=%lld p=%lld", (long long)n,
+  SAB_REQUIRE(n >= 0 && p > 0 && p < (1ll << 30) && ldx >= p && (out == nullptr || ldo >= p), "bad shape n=%lld p=%lld", (long long)n,
               (long long)p);
-  SAB_REQUIRE(out != nullptr, "NULL output");
+  SAB_REQUIRE(out != nullptr || rownorm_sum != nullptr, "NULL output");
   if (n == 0) return 0;
   int dev = 0, sms = 0;
   SAB_CHECK_CUDA(cudaGetDevice(&dev));
@@ -182,7 +182,7 @@ extern "C" int sa_transform_rows(void* stream, const float* X, int64_t n, int64_
   long long blocks = ceil_div(n, pre::TR_WARPS);
   if (blocks > static_cast<long long>(sms) * 8) blocks = static_cast<long long>(sms) * 8;
   const bool vec = (ldx % 4 == 0) && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                   (out == nullptr || (reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
                    (!shift || (reinterpret_cast<uintptr_t>(shift) & 15) == 0) &&
                    (!scale || (reinterpret_cast<uintptr_t>(scale) & 15) == 0);
   if (vec)

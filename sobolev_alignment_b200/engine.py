@@ -144,6 +144,9 @@ class CudaOps:
         n, p = X.shape
         if out is not None and (out.n != n or out.p != p):
             raise ValueError("prepared buffer does not match the rows to prepare")
+        if hasattr(X, "folded"):      # preprocessing.DeferredRows: counts -> fp16 rows + norms in one pass
+            shift, scale = X.folded(frame.shift, frame.scale)
+            return nat.prep(X.counts, shift, scale, frame.gscale, out=out, log10p1=X.log10p1)
         if X.is_cuda:
             Xd = X if X.dtype == torch.float32 and X.stride(1) == 1 else X.float().contiguous()
             return nat.prep(Xd, frame.shift, frame.scale, frame.gscale, out=out)

@@ -89,7 +89,8 @@ class Falkon:
     def fit(self, X: torch.Tensor, Y: torch.Tensor, Xts=None, Yts=None, warm_start=None):
         if warm_start is not None:
             raise NotImplementedError("warm_start is not supported")
-        X, Y = torch.as_tensor(X), torch.as_tensor(Y)
+        deferred = hasattr(X, "folded")      # preprocessing.DeferredRows: counts + the affine map still to apply
+        X, Y = (X if deferred else torch.as_tensor(X)), torch.as_tensor(Y)
         if X.dim() != 2:
             raise ValueError("X must be 2-dimensional")
         if Y.dim() == 1:
@@ -107,12 +108,14 @@ class Falkon:
             centres, n_total = self._gather_centres(X, comm, ops)
         else:
             idx = self._select_centres(n_local)
-            centres = X[torch.from_numpy(idx).to(X.device)]
+            centres = X.rows(idx) if deferred else X[torch.from_numpy(idx).to(X.device)]
             n_total = n_local
         # Row-sharded fit from host inputs: `ny_points_` has to be a host tensor again (anchors() contract).
         # Its 600 MB read-back (C3) runs on a helper thread / side stream while the solver works.
+        # results live where the inputs live; deferred rows always sit on the device, so Y decides for them
+        on_device = Y.is_cuda if deferred else X.is_cuda
         fetch = None
-        if centres.is_cuda and not X.is_cuda:
+        if centres.is_cuda and not on_device:
             fetch = _HostFetch(centres)
         solver = FalkonSolver(ops, self.kernel.spec(), self.penalty, self.maxiter, pc_eps=opt.pc_eps(),
                               cg_eps=float(opt.cg_epsilon_32), cg_tol=float(opt.cg_tolerance),
@@ -121,11 +124,11 @@ class Falkon:
         self.solver_stats_ = {"times": dict(solver.times), "residuals": list(solver.residuals),
                               "n_iter": solver.n_iter_, "n_kmv": solver.n_kmv_, "n_total": n_total}
         solver.release()
-        self.alpha_ = alpha.to(Y.dtype) if X.is_cuda else alpha.to(Y.dtype).cpu()
+        self.alpha_ = alpha.to(Y.dtype) if on_device else alpha.to(Y.dtype).cpu()
         if fetch is not None:
             self.ny_points_ = fetch.result()
         else:
-            self.ny_points_ = centres if centres.device == X.device else centres.to(X.device)
+            self.ny_points_ = centres if centres.is_cuda == on_device else (centres.cuda() if on_device else centres.cpu())
         self.fit_times_ = [time.perf_counter() - t0]
         self._predictor = None
         if self.error_fn is not None and Xts is not None and Yts is not None:
@@ -149,7 +152,7 @@ class Falkon:
                              "all ranks draw the same centres")
         idx = self._select_centres(n_total)
         mine = idx[(idx >= offsets[comm.rank]) & (idx < offsets[comm.rank + 1])] - offsets[comm.rank]
-        rows = ops.to_device(X[torch.from_numpy(mine).to(X.device)])
+        rows = X.rows(mine) if hasattr(X, "folded") else ops.to_device(X[torch.from_numpy(mine).to(X.device)])
         p = X.shape[1]
         full = ops.zeros(len(idx), p)
         pos = np.nonzero((idx >= offsets[comm.rank]) & (idx < offsets[comm.rank + 1]))[0]

@@ -21,6 +21,63 @@ import torch
 from . import _native as nat
 
 
+class DeferredRows:
+    """
+    Rows whose preprocessing has been DECIDED but not applied: raw counts resident on the device plus the
+    affine map that follows the log,  y = (log10(x + 1) - shift) * scale * gain.  `KRRApprox(method="falkon").fit`
+    / `Falkon.fit` take it in place of the fp32 tensor: the map is folded into the operand preparation
+    (`sa_prep_log`: counts -> fp16 rows + norms in ONE pass), so the preprocessed fp32 matrix (12 GB at
+    BASELINE config 3) is never written.  Only the M centre rows are materialised (`rows`), because
+    `anchors()` has to hand them back.
+    """
+
+    is_cuda = True
+    dtype = torch.float32
+
+    def __init__(self, counts: torch.Tensor, log10p1: bool, shift, scale, gain: float):
+        self.counts, self.log10p1 = counts, bool(log10p1)
+        self.shift, self.scale, self.gain = shift, scale, float(gain)
+
+    @property
+    def shape(self):
+        return self.counts.shape
+
+    @property
+    def device(self):
+        return self.counts.device
+
+    def dim(self):
+        return 2
+
+    def rows(self, idx) -> torch.Tensor:
+        """Materialised preprocessed rows idx (float32 CUDA tensor)."""
+        idx = torch.as_tensor(idx, device=self.counts.device)
+        out = self.counts[idx].contiguous()
+        nat.transform_rows(out, self.log10p1, self.shift, self.scale, self.gain)
+        return out
+
+    def materialize(self) -> torch.Tensor:
+        out = self.counts.clone()
+        nat.transform_rows(out, self.log10p1, self.shift, self.scale, self.gain)
+        return out
+
+    def folded(self, frame_shift, frame_scale):
+        """
+        (shift', scale') with  ((f(x) - shift) scale gain - frame_shift) frame_scale == (f(x) - shift') scale'
+        per column: what `sa_prep_log` needs next to the frame's power-of-two gain.
+        """
+        p = self.counts.shape[1]
+        dev = self.counts.device
+        a = torch.full((p,), self.gain, dtype=torch.float64, device=dev)          # y = (f - shift) a
+        if self.scale is not None:
+            a = a * self.scale.double()
+        sh = torch.zeros(p, dtype=torch.float64, device=dev) if self.shift is None else self.shift.double()
+        fs = torch.zeros(p, dtype=torch.float64, device=dev) if frame_shift is None else frame_shift.double()
+        sc = a if frame_scale is None else a * frame_scale.double()
+        shift = sh + fs / a
+        return shift.float().contiguous(), sc.float().contiguous()
+
+
 class InputPreprocessor:
     def __init__(self, log_input: bool = False, mean_center: bool = False, unit_std: bool = False,
                  frob_norm_source: bool = False, device=None, chunk_rows: int = 65536):
@@ -68,6 +125,18 @@ class InputPreprocessor:
     # ------------------------------------------------------------------ the chain
     def fit_transform(self, data_source: str, X) -> torch.Tensor:
         """X: counts [n x p] (numpy / memmap / CPU or CUDA tensor).  Returns a float32 CUDA tensor [n x p]."""
+        return self._run(data_source, X, deferred=False)
+
+    def fit_prepare(self, data_source: str, X) -> DeferredRows:
+        """
+        Same statistics as `fit_transform` (column mean / variance, mean row norm), but the transform itself is
+        deferred: the result feeds `KRRApprox.fit` directly and the chain runs inside the operand preparation.
+        Passes over the resident counts: column statistics, row norms (Frobenius only), and later the single
+        counts -> fp16 pass; nothing is written back.
+        """
+        return self._run(data_source, X, deferred=True)
+
+    def _run(self, data_source: str, X, deferred: bool):
         if data_source not in ("source", "target"):
             raise ValueError("data_source must be 'source' or 'target'")
         Xd = self._to_device(X)
@@ -87,9 +156,10 @@ class InputPreprocessor:
             self.mean_[data_source] = mean if self.mean_center else None
             self.scale_[data_source] = sd if self.unit_std else None
         need_norm = self.frob_norm_source
+        gain = 1.0
         if self.log_input or need_norm:
             norm_sum = nat.transform_rows(Xd, log10p1=self.log_input, shift=shift, scale=scale, gain=1.0,
-                                          want_row_norms=need_norm)
+                                          want_row_norms=need_norm, in_place=not deferred)
         if need_norm and n > 0:
             mean_norm = float(norm_sum) / n
             if data_source == "source":
@@ -97,5 +167,9 @@ class InputPreprocessor:
             else:
                 if self.frob_norm_param_ is None:
                     raise RuntimeError("frob_norm_source: the source must be processed before the target")
-                nat.axpby(self.frob_norm_param_ / mean_norm, Xd.view(-1), 0.0, Xd.view(-1))
+                gain = self.frob_norm_param_ / mean_norm
+                if not deferred:
+                    nat.axpby(gain, Xd.view(-1), 0.0, Xd.view(-1))
+        if deferred:
+            return DeferredRows(Xd, self.log_input, shift, scale, gain)
         return Xd

@@ -255,7 +255,7 @@ class FalkonSolver:
         del C
         # Host inputs are staged (pinned copy, H2D, fp16 preparation) on a side stream WHILE the main
         # stream factorises the preconditioner, which only needs the centres.
-        overlap = hasattr(ops, "staging_stream") and not (torch.is_tensor(X) and X.is_cuda)
+        overlap = hasattr(ops, "staging_stream") and not getattr(X, "is_cuda", False)
         if overlap:
             main = torch.cuda.current_stream(ops.device)
             side = ops.staging_stream()

@@ -149,6 +149,54 @@ def test_input_preprocessor_matches_oracle(log_input, mean_center, unit_std, fro
     assert np.array_equal(np.load(path), src)           # the input was not written
 
 
+def test_fused_preprocessing_feeds_the_fit_without_the_fp32_intermediate():
+    """
+    InputPreprocessor.fit_prepare: the chain log10(x + 1) -> StandardScaler -> Frobenius gain folded into the
+    operand preparation (sa_prep_log).  The prepared fp16 rows / norms equal those of the two-step route, the
+    materialised rows equal the oracle chain, and a fit on the deferred rows equals the fit on the fp32 tensor.
+    """
+    from oracle.preprocess_oracle import PreprocessOracle
+    from sobolev_alignment_b200 import KRRApprox, _native as nat
+    from sobolev_alignment_b200.engine import CudaOps, KernelSpec
+    from sobolev_alignment_b200.preprocessing import InputPreprocessor
+
+    rng = np.random.default_rng(23)
+    p = 333
+    rates = rng.integers(1, 25, size=p)
+    src = rng.poisson(rates[None, :] * rng.lognormal(0, 0.25, size=(3001, 1))).astype(np.float32)
+    tgt = rng.poisson(rates[None, :] * rng.lognormal(0, 0.3, size=(2500, 1))).astype(np.float32)
+    two_step, fused = InputPreprocessor(True, True, True, True), InputPreprocessor(True, True, True, True)
+    orc = PreprocessOracle(True, True, True, True)
+    ops = CudaOps()
+    for name, data in (("source", src), ("target", tgt)):
+        full = two_step.fit_transform(name, data)
+        lazy = fused.fit_prepare(name, data)
+        ref = orc.fit_transform(name, data)
+        assert torch.equal(lazy.counts.cpu(), torch.from_numpy(data))          # counts untouched, nothing written back
+        assert relerr(lazy.materialize(), torch.from_numpy(ref)) < 1e-5
+        idx = np.arange(0, data.shape[0], 7)
+        assert relerr(lazy.rows(idx), torch.from_numpy(ref[idx])) < 1e-5
+        frame = ops.make_frame(full[:256], KernelSpec("laplacian", 10.0))
+        a, b = ops.prepare(full, frame), ops.prepare(lazy, frame)
+        # same fp16 operand up to last-bit rounding of the folded affine map
+        diff = (a.data.float() - b.data.float()).abs()
+        assert float(diff.max()) <= 2e-3 * float(a.data.float().abs().max()) and float((diff > 0).float().mean()) < 0.02
+        assert relerr(b.norms, a.norms.double()) < 1e-4
+    assert abs(fused.frob_norm_param_ / two_step.frob_norm_param_ - 1) < 1e-6
+    # a fit on the deferred rows == the fit on the materialised tensor
+    Y = torch.from_numpy(syn.targets_numpy(orc.fit_transform("target", tgt), 4, seed=3))
+    fits = []
+    for X in (full, lazy):
+        clf = KRRApprox(method="falkon", kernel="laplacian", kernel_params={"sigma": 15.0}, penalization=1e-4, M=300,
+                        falkon_options={"center_seed": 9})
+        clf.fit(X, Y.cuda() if torch.is_tensor(X) else Y)
+        fits.append(clf)
+    assert not fits[1].sample_weights_.is_cuda and not fits[1].anchors().is_cuda   # Y on the host -> host results
+    assert relerr(fits[1].anchors(), fits[0].anchors().cpu().double()) < 1e-5
+    Xv = full[:64]
+    assert relerr(fits[1].transform(Xv.cpu()), fits[0].transform(Xv).cpu().double()) < 1e-3
+
+
 # ---------------------------------------------------------------------------- fused kmv
 @pytest.mark.parametrize("family,okernel,nu", FAMILIES)
 @pytest.mark.parametrize("a,b,p,d", [(1, 1, 1, 1), (128, 256, 64, 4), (300, 500, 100, 7), (2000, 500, 500, 10),
