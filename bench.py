@@ -47,11 +47,20 @@ WORKLOADS = {
     "C4": (2_000_000, 3000, 100_000, 20, "matern", {"sigma": 10.0, "nu": 1.5}, 1e-6),
 }
 MAXITER = 20
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel (ncu --set full), mean of the
-# forward (77.3 GB) and transposed (87.9 GB) C3 launches; the tensor-bound kernel re-reads its fp16 operands
-# (6.3 GB) ~13 times through L2-sized windows, which is 5 % of the HBM bandwidth over the launch
-KMV_TRAFFIC = {("C3", 1): 82.6e9}
-KMV_TRAFFIC_SOURCE = "profiles/r01_kmv_v9_c3_ncu.txt + r01_kmv_v8_c3_*_ncu_full.txt (bytes per launch)"
+
+
+def kmv_traffic(cfg_name, world):
+    """
+    dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel, from the committed ncu
+    capture (profiles/kmv_traffic.json: {"<workload>@<gpus>": {"bytes_per_launch": ..., "source": ...}}); None
+    when no capture exists for this workload -- the number is never made up in this file.
+    """
+    path = os.path.join(ROOT, "profiles", "kmv_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        ent = json.load(f).get(f"{cfg_name}@{world}")
+    return (ent["bytes_per_launch"], ent["source"]) if ent else (None, None)
 
 
 def measured_peaks():
@@ -185,6 +194,225 @@ def workload_config(cfg_name, gpus):
 
 
 # --------------------------------------------------------------------------------------------------
+# secondary legs: extra keys of the one JSON line (the C3 fit stays the headline); every leg is bounded
+# and fenced by try/except so that it can never cost the headline its line
+def _events():
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def leg_c2(dev, args):
+    """BASELINE config 2 (n=1e5, p=2000, M=1e4, d=10) fit, device-resident, + the COMPLETE float32 CPU fit beside it."""
+    from oracle import falkon_oracle as fo
+    from sobolev_alignment_b200 import KRRApprox, _native as nat, synthetic as syn
+    from sobolev_alignment_b200.falkon import Falkon, FalkonOptions
+
+    n, p, M, d, kernel, kparams, lam = WORKLOADS["C2"]
+    X = syn.log_counts_torch(n, p, seed=2000, device=dev)
+    Y = syn.targets_torch(X, d, seed=7)
+    kobj = KRRApprox.falkon_kernel[kernel](**kparams)
+
+    def fit():
+        return Falkon(kernel=kobj, penalty=lam, M=M, maxiter=MAXITER, options=FalkonOptions(center_seed=11)).fit(X, Y)
+
+    for _ in range(2):
+        fit()
+    nat.STATS.reset()
+    nat.STATS.time_kmv = True
+    torch.cuda.synchronize()
+    e0, e1 = _events()
+    e0.record()
+    reps = 5
+    for _ in range(reps):
+        est = fit()
+    e1.record()
+    torch.cuda.synchronize()
+    nat.STATS.time_kmv = False
+    fl, ks, kn = nat.STATS.kmv_summary()
+    out = {"fit_s": e0.elapsed_time(e1) / reps / 1e3, "kmv_tflops": fl / ks / 1e12 if ks else None,
+           "phases_s": est.solver_stats_["times"], "workload": workload_config("C2", 1)["workload"]}
+    if not args.no_cpu_baseline:
+        Xc, Yc = X.cpu(), Y.cpu()
+        idx = np.sort(np.random.default_rng(11).choice(n, size=M, replace=False))
+        torch.set_num_threads(os.cpu_count() or 1)
+        t = time.perf_counter()
+        fo.falkon_fit_f32(Xc, Yc, Xc[idx], kernel, kparams["sigma"], lam, maxiter=MAXITER)
+        out["cpu_fit_s"] = time.perf_counter() - t
+        out["cpu"] = f"complete float32 CPU port fit, all {n} rows, {os.cpu_count()} cores, not extrapolated"
+    return out
+
+
+def leg_transform(est, Xh, label):
+    """`transform` throughput (row a9): K(X, C) alpha for host rows, staging inside the timed region."""
+    est.predict(Xh[:131072])                       # warm-up: predictor (prepared centres), staging buffers
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    out = est.predict(Xh)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t
+    n, p = Xh.shape
+    M, d = est.alpha_.shape
+    return {"rows_per_s": n / dt, "seconds": dt, "n": n, "M": M, "d": d, "input": label,
+            "tflops_incl_staging": 2.0 * n * M * (p + d) / dt / 1e12, "h2d_bytes": n * p * 4, "d2h_bytes": int(out.numel() * 4)}
+
+
+def leg_memmap_e2e(one_fit, Xh, Yh, est_for_transform):
+    """
+    The e2e fit with the input the reference REALLY hands over: torch.from_numpy of a read-only np.memmap
+    (pageable, file-backed; sobolev_alignment.py:613-616,922-925) -- the backend has to stage it through its own
+    pinned buffers.  The file lives on /dev/shm when that has room (page-cache speed), else in the temp dir.
+    """
+    import shutil
+    import tempfile
+    import warnings
+
+    n, p = Xh.shape
+    need = n * p * 4 + (1 << 30)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > need else tempfile.gettempdir()
+    if shutil.disk_usage(base).free < need:
+        return {"skipped": f"no room for a {need >> 30} GiB memmap under {base}"}
+    d = tempfile.mkdtemp(prefix="sab_bench_", dir=base)
+    try:
+        path = os.path.join(d, "X.npy")
+        mm = np.lib.format.open_memmap(path, mode="w+", dtype=np.float32, shape=(n, p))
+        step = 1 << 16
+        for s0 in range(0, n, step):
+            mm[s0: s0 + step] = Xh[s0: s0 + step].numpy()
+        mm.flush()
+        del mm
+        ro = np.load(path, mmap_mode="r")
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)       # "non-writable array": it is never written
+            Xm = torch.from_numpy(ro)
+        Ym = Yh.clone()                                        # pageable
+        e0, e1 = _events()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        e0.record()
+        est = one_fit(Xm, Ym, through_krr_approx=True)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t
+        out = {"value": e0.elapsed_time(e1) / 1e3, "unit": "s", "wall_s": wall, "input": f"read-only np.memmap under {base}",
+               "phases_s": est.solver_stats_["times"], "h2d_bytes_per_step": int(n * p * 4 + Ym.numel() * 4)}
+        out["transform"] = leg_transform(est_for_transform, Xm, f"read-only np.memmap under {base}")
+        return out
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def leg_c5(dev):
+    """
+    BASELINE config 5: source + target KRR fits with M = 50k centres each, then the cross-kernel products
+    M_X, M_Y, M_XY (alpha^T K beta through the fused kernel, no M x M matrix) and the principal-vector cosines.
+    n = 250 000 artificial samples per side (BASELINE.json does not fix n for this config), p = 3000, d = 20.
+    """
+    from sobolev_alignment_b200 import KRRApprox, synthetic as syn
+    from sobolev_alignment_b200.alignment import EncoderComparison
+
+    n, p, M, d = 250_000, 3000, 50_000, 20
+    krr, fit_s = {}, {}
+    for i, side in enumerate(("source", "target")):
+        X = syn.log_counts_torch(n, p, seed=3000 + i, device=dev)
+        Y = syn.targets_torch(X, d, seed=7)
+        clf = KRRApprox(method="falkon", kernel="laplacian", kernel_params={"sigma": 10.0}, M=M, penalization=1e-6,
+                        maxiter=MAXITER, falkon_options={"center_seed": 21 + i})
+        e0, e1 = _events()
+        e0.record()
+        clf.fit(X, Y)
+        e1.record()
+        torch.cuda.synchronize()
+        fit_s[side] = e0.elapsed_time(e1) / 1e3
+        krr[side] = clf
+        del X, Y
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    cmp_ = EncoderComparison(krr["source"], krr["target"]).compare().principal_vectors()
+    torch.cuda.synchronize()
+    align_s = time.perf_counter() - t
+    return {"fit_s": fit_s, "cross_kernels_and_cosines_s": align_s, "total_s": sum(fit_s.values()) + align_s,
+            "top_principal_cosines": [float(x) for x in cmp_.principal_angles[:5]],
+            "workload": f"two KRRApprox Falkon-path fits (n={n}, p={p}, M={M}, d={d}, laplacian sigma 10) + M_X/M_Y/M_XY + SVD"}
+
+
+def leg_baseline_b():
+    """BASELINE.md Baseline B: the reference's OWN KRRApprox(method='sklearn') at config 1 (exact KRR, CPU)."""
+    import importlib.util
+
+    from sobolev_alignment_b200 import synthetic as syn
+
+    path = os.path.join(ROOT, "baseline", "_ref", "sobolev_alignment", "krr_approx.py")
+    if not os.path.exists(path):
+        return {"skipped": "unmodified reference not installed (oracle/install_reference.sh)"}
+    spec = importlib.util.spec_from_file_location("ref_krr_approx_bench", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    n, p, M, d, kernel, kparams, lam = WORKLOADS["C1"]
+    Xn = syn.log_counts_numpy(n, p, seed=0)
+    X, Y = torch.from_numpy(Xn), torch.from_numpy(syn.targets_numpy(Xn, d, seed=1, linear=True))
+    times = []
+    for _ in range(3):
+        clf = mod.KRRApprox(method="sklearn", kernel="matern", kernel_params={"length_scale": 10.0, "nu": 0.5},
+                            penalization=lam)
+        t = time.perf_counter()
+        clf.fit(X, Y)
+        times.append(time.perf_counter() - t)
+    return {"fit_s": float(np.median(times)), "what": "reference krr_approx.py KRRApprox(method='sklearn', kernel='matern', "
+            f"nu=0.5 (= L2 Laplacian)) fit at C1 (n={n}, p={p}, d={d}), {os.cpu_count()} cores"}
+
+
+def leg_c1(dev):
+    """BASELINE config 1 on the GPU through the same API (n=2000, p=500, M=500, d=10): launch-latency bound."""
+    from sobolev_alignment_b200 import KRRApprox, synthetic as syn
+
+    n, p, M, d, kernel, kparams, lam = WORKLOADS["C1"]
+    Xn = syn.log_counts_numpy(n, p, seed=0)
+    X, Y = torch.from_numpy(Xn), torch.from_numpy(syn.targets_numpy(Xn, d, seed=1, linear=True))
+    times = []
+    for _ in range(4):
+        clf = KRRApprox(method="falkon", kernel=kernel, kernel_params=kparams, M=M, penalization=lam, maxiter=MAXITER)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        clf.fit(X, Y)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t)
+    return {"fit_s": float(np.median(times[1:])), "what": "KRRApprox(method='falkon') fit at C1, host inputs, wall clock"}
+
+
+def leg_c4(dev, rank, world, timed, barrier):
+    """BASELINE config 4: Matern nu=1.5, n=2M, M=100k, d=20 on 8 GPUs (row shards + per-iteration all-reduce)."""
+    from sobolev_alignment_b200 import KRRApprox, _native as nat, synthetic as syn
+    from sobolev_alignment_b200.falkon import Falkon, FalkonOptions
+
+    n, p, M, d, kernel, kparams, lam = WORKLOADS["C4"]
+    bounds = np.linspace(0, n, world + 1).astype(np.int64)
+    n_local = int(bounds[rank + 1] - bounds[rank])
+    X = syn.log_counts_torch(n_local, p, seed=4000 + rank, device=dev)
+    Y = syn.targets_torch(X, d, seed=7)
+    kobj = KRRApprox.falkon_kernel[kernel](**kparams)
+
+    def fit():
+        return Falkon(kernel=kobj, penalty=lam, M=M, maxiter=MAXITER,
+                      options=FalkonOptions(row_sharded=world > 1, center_seed=11)).fit(X, Y)
+
+    fit()                                               # warm-up
+    nat.STATS.reset()
+    nat.STATS.time_kmv = True
+    ms, wall, est = timed(fit, 2)
+    nat.STATS.time_kmv = False
+    fl, ks, kn = nat.STATS.kmv_summary()
+    tb, ts, tn = nat.STATS.trsm_summary()
+    return {"fit_s": ms / 1e3, "steps": 2, "kmv_tflops_per_gpu": fl / ks / 1e12 if ks else None,
+            "trsm_gbs": tb / ts / 1e9 if ts else None, "phases_s": est.solver_stats_["times"],
+            "final_residual": est.solver_stats_["residuals"][-1], "workload": workload_config("C4", world)["workload"]}
+
+
+def _guard(fn, *a, **k):
+    try:
+        return fn(*a, **k)
+    except Exception as exc:  # noqa: BLE001 - a secondary leg must not cost the headline its line
+        return {"error": f"{type(exc).__name__}: {exc}"[:400]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -195,6 +423,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-sample", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary legs (C1/C2/C4/C5, transform, memmap)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -279,12 +508,13 @@ def main():
 
     # ---------------- end-to-end arm: pinned host inputs through KRRApprox.fit
     e2e = None
+    extras_host = {}
     if not args.no_e2e:
         Xh = torch.empty(n_local, p, dtype=torch.float32).pin_memory()
         Yh = torch.empty(n_local, d, dtype=torch.float32).pin_memory()
         Xh.copy_(X)
         Yh.copy_(Y)
-        del X, Y
+        X = Y = None
         torch.cuda.empty_cache()
         one_fit(Xh, Yh, through_krr_approx=True)   # warm-up (pinned staging buffers, allocator)
         e2e_ms, e2e_wall, est2 = timed(lambda: one_fit(Xh, Yh, through_krr_approx=True), max(1, min(args.steps, 2)))
@@ -294,7 +524,18 @@ def main():
                "api": "KRRApprox(method='falkon').fit(X_host_pinned, Y_host_pinned)",
                "stage_inputs_s": est2.solver_stats_["times"].get("stage_inputs"),
                "phases_s": est2.solver_stats_["times"], "host_overhead_s": e2e_wall / 1e3 - est2.solver_stats_["times"]["fit"]}
+        extras_host = {}
+        if not args.no_extras and world == 1 and cfg_name == "C3":
+            extras_host["transform"] = _guard(leg_transform, est2, Xh, "pinned host tensor")
+            extras_host["e2e_memmap"] = _guard(leg_memmap_e2e, one_fit, Xh, Yh, est2)
+        del Xh, Yh
+        torch.cuda.empty_cache()
 
+    c4 = None
+    if not args.no_extras and world == 8 and cfg_name == "C3":
+        X = Y = est = None
+        torch.cuda.empty_cache()
+        c4 = _guard(leg_c4, dev, rank, world, timed, barrier)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -309,8 +550,8 @@ def main():
         "config": workload_config(cfg_name, world),
         "roofline": {"bound": "tensor", "kernel": "kmv_kernel (fused tcgen05 K(A,B)@V)", "achieved": kmv_tflops,
                      "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": kmv_tflops / peaks["bf16_sustained"], "traffic": KMV_TRAFFIC.get((cfg_name, world)),
-                     "traffic_source": KMV_TRAFFIC_SOURCE if (cfg_name, world) in KMV_TRAFFIC else None,
+                     "frac": kmv_tflops / peaks["bf16_sustained"], "traffic": kmv_traffic(cfg_name, world)[0],
+                     "traffic_source": kmv_traffic(cfg_name, world)[1],
                      "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                      "launches_timed": kmv_n, "kmv_seconds_per_fit": kmv_s / max(1, args.steps),
                      "algorithmic_flops_per_fit": kmv_flops / max(1, args.steps)},
@@ -322,6 +563,19 @@ def main():
         "wall_ms_per_step": wall_ms, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
     }
 
+    if e2e is not None and "e2e_memmap" in extras_host:
+        e2e["memmap"] = extras_host["e2e_memmap"]
+    if "transform" in extras_host:
+        line["transform"] = extras_host["transform"]
+    if c4 is not None:
+        line["c4"] = c4
+    if not args.no_extras and world == 1 and cfg_name == "C3":
+        torch.cuda.empty_cache()
+        line["c2"] = _guard(leg_c2, dev, args)
+        line["c5"] = _guard(leg_c5, dev)
+        line["c1"] = _guard(leg_c1, dev)
+        if not args.no_cpu_baseline:
+            line["c1"]["reference_sklearn"] = _guard(leg_baseline_b)
     if not args.no_cpu_baseline:
         ref = reference_arm(argparse.Namespace(gpus=world, steps=1, warmup=1, force_sample=args.force_sample), cfg_name)
         line["cpu_baseline"] = ref["cpu_baseline"]
