@@ -104,6 +104,24 @@ int sa_kmv(void* stream, int kernel, float kscale, const void* A, const float* n
            int64_t workspace_bytes);
 
 /*
+ * Optional "stored block" form of one K_nM^T (K_nM z) product (falkon keeps K_nM when it fits --
+ * `FalkonOptions.never_store_kernel = False`, krr_model_selection.py:56 -- here it is a transient ROW BLOCK):
+ *   sa_kmv_store  as sa_kmv, and the kernel block k(A, B) is also written to `kstore` as fp16 hi/lo pairs in
+ *                 packed 128 x 128 tiles (4 bytes per entry; sa_kstore_bytes(a, b) bytes, 128-byte aligned)
+ *   sa_ktv        out[b x dp] += k(A, B)^T t  streamed from that store (HBM-bound: the block is read once)
+ *                 instead of forming K a second time; t [a x dp] fp32; workspace sa_ktv_workspace_bytes(a).
+ * The default path never materialises K (sa_kmv twice per product pair).
+ */
+int64_t sa_kstore_bytes(int64_t a, int64_t b);
+int sa_kmv_store(void* stream, int kernel, float kscale, const void* A, const float* nA, int64_t a,
+                 int64_t lda, const void* B, const float* nB, int64_t b, int64_t ldb, int64_t p_pad,
+                 const float* V, int dp, float* out, void* workspace, int64_t workspace_bytes, void* kstore,
+                 int64_t kstore_bytes);
+int64_t sa_ktv_workspace_bytes(int64_t a);
+int sa_ktv(void* stream, const void* kstore, int64_t a, int64_t b, const float* t, int dp, float* out,
+           void* workspace, int64_t workspace_bytes);
+
+/*
  * Dense kernel matrix (falkon `Kernel.__call__` [ext]; called as `kernel_(A, B)` at
  * sobolev_alignment.py:950,955-958 and tests/test_krr_approx.py:255, and for K_MM inside
  * `Falkon.fit`):  out[a x b] = k(A, B), fp32, row stride ldo.

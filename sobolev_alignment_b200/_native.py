@@ -43,12 +43,18 @@ class LaunchStats:
         self.launches = 0
         self.kmv_events = []   # (flops, start_event, end_event)
         self.trsm_events = []  # (bytes, start_event, end_event)
+        self.ktv_events = []   # (bytes, start_event, end_event)
 
     def kmv_summary(self):
         """(total algorithmic flops, total seconds, launches) over the recorded fused-kernel launches."""
         fl = sum(f for f, _, _ in self.kmv_events)
         ms = sum(a.elapsed_time(b) for _, a, b in self.kmv_events)
         return fl, ms * 1e-3, len(self.kmv_events)
+
+    def ktv_summary(self):
+        by = sum(f for f, _, _ in self.ktv_events)
+        ms = sum(a.elapsed_time(b) for _, a, b in self.ktv_events)
+        return by, ms * 1e-3, len(self.ktv_events)
 
     def trsm_summary(self):
         by = sum(f for f, _, _ in self.trsm_events)
@@ -76,6 +82,12 @@ _SIGNATURES = {
     "sa_kmv_workspace_bytes": (c_int64, [c_int64, c_int]),
     "sa_kmv": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
                        c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64]),
+    "sa_kstore_bytes": (c_int64, [c_int64, c_int64]),
+    "sa_kmv_store": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                             c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                             c_int64]),
+    "sa_ktv_workspace_bytes": (c_int64, [c_int64]),
+    "sa_ktv": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_int64]),
     "sa_kdense": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                           c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int]),
     "sa_linalg_workspace_bytes": (c_int64, [c_int64]),
@@ -181,6 +193,10 @@ class Prepared:
     def __init__(self, data, norms, n, p):
         self.data, self.norms, self.n, self.p, self.p_pad = data, norms, n, p, data.shape[1]
 
+    def rows(self, r0: int, r1: int) -> "Prepared":
+        """View of rows [r0, r1) as the A operand of a fused product (r0 a multiple of 128)."""
+        return Prepared(self.data[r0:r1], self.norms[r0:], r1 - r0, self.p)
+
     def head(self, m: int) -> "Prepared":
         """View of the first m rows (the norm padding of the view is re-zeroed by the prep that fills it)."""
         return Prepared(self.data[:m], self.norms[: round_up(max(m, 1), NORM_PAD)], m, self.p)
@@ -282,8 +298,12 @@ def _workspace(device, nbytes: int) -> torch.Tensor:
 
 
 def kmv(kernel_id: int, kscale: float, A: Prepared, B: Prepared, V: torch.Tensor, out: torch.Tensor,
-        symmetric: bool = False):
-    """out[a x dp] += k(A, B) @ V[b x dp]   (out must be zeroed by the caller for a plain product)."""
+        symmetric: bool = False, kstore: torch.Tensor | None = None):
+    """
+    out[a x dp] += k(A, B) @ V[b x dp]   (out must be zeroed by the caller for a plain product).
+    `kstore` (uint8, >= kstore_bytes(a, b)): the kernel block is also left behind as packed fp16 hi/lo tiles for
+    `ktv` (sa_kmv_store).
+    """
     lib = load()
     _req(V, torch.float32, "V")
     _req(out, torch.float32, "out")
@@ -300,14 +320,43 @@ def kmv(kernel_id: int, kscale: float, A: Prepared, B: Prepared, V: torch.Tensor
     if nbytes < 0:
         raise NativeLibraryError(f"dp must be a multiple of 4 in [4, 32], got {dp}")
     ws = _workspace(V.device, nbytes)
-    _call(lib.sa_kmv, V.device, kernel_id, float(kscale), A.data.data_ptr(), A.norms.data_ptr(), A.n,
-                      A.p_pad, B.data.data_ptr(), B.norms.data_ptr(), B.n, B.p_pad, A.p_pad,
-                      V.data_ptr(), dp, out.data_ptr(), int(symmetric), ws.data_ptr(), ws.numel())
+    if kstore is None:
+        _call(lib.sa_kmv, V.device, kernel_id, float(kscale), A.data.data_ptr(), A.norms.data_ptr(), A.n,
+              A.p_pad, B.data.data_ptr(), B.norms.data_ptr(), B.n, B.p_pad, A.p_pad,
+              V.data_ptr(), dp, out.data_ptr(), int(symmetric), ws.data_ptr(), ws.numel())
+    else:
+        _call(lib.sa_kmv_store, V.device, kernel_id, float(kscale), A.data.data_ptr(), A.norms.data_ptr(), A.n,
+              A.p_pad, B.data.data_ptr(), B.norms.data_ptr(), B.n, B.p_pad, A.p_pad,
+              V.data_ptr(), dp, out.data_ptr(), ws.data_ptr(), ws.numel(), kstore.data_ptr(), kstore.numel())
     if ev is not None:
         ev[1].record(torch.cuda.current_stream(V.device))
         # algorithmic work: 2 a b p + 2 a b d, with the caller's p and padded d
         STATS.kmv_events.append((2.0 * A.n * B.n * (A.p + dp), ev[0], ev[1]))
     STATS.launches += 3   # column maxima, fp16 split of V, fused kernel
+    return out
+
+
+def kstore_bytes(a: int, b: int) -> int:
+    return int(load().sa_kstore_bytes(a, b))
+
+
+def ktv(kstore: torch.Tensor, a: int, b: int, t: torch.Tensor, out: torch.Tensor):
+    """out[b x dp] += k(A, B)^T t[a x dp] from the block a previous kmv(..., kstore=) left behind."""
+    _req(t, torch.float32, "t")
+    _req(out, torch.float32, "out")
+    dp = t.shape[1]
+    if t.shape[0] != a or out.shape != (b, dp):
+        raise ValueError(f"shape mismatch: t {tuple(t.shape)}, out {tuple(out.shape)}, a={a}, b={b}")
+    ev = None
+    if STATS.time_kmv:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record(torch.cuda.current_stream(t.device))
+    ws = _workspace(t.device, int(load().sa_ktv_workspace_bytes(a)))
+    _call(load().sa_ktv, t.device, kstore.data_ptr(), a, b, t.data_ptr(), dp, out.data_ptr(), ws.data_ptr(), ws.numel())
+    if ev is not None:
+        ev[1].record(torch.cuda.current_stream(t.device))
+        STATS.ktv_events.append((4.0 * a * b, ev[0], ev[1]))     # the stored block is read once: 4 bytes per entry
+    STATS.launches += 2
     return out
 
 

@@ -123,6 +123,12 @@ struct Params {
   float alpha, gamma;  // MODE_GEMM: out = gamma * out + alpha * alpha_dev[0] * A B^T
   const float* alpha_dev;  // optional device-side factor of alpha (NULL = 1)
   int lower;           // MODE_GEMM: only tiles that touch the lower triangle (col <= row) are computed
+  uint8_t* kstore;   // MODE_KMV, optional: the kernel block k(A, B) 2^14 is ALSO written out, as fp16 hi / lo
+                     // (lo x 2^11) pairs in the packed 128 x 128 tile image of the triangular solves (trsm.cu):
+                     // tile (row block, column block) at (rb * kstore_nj + cb) * 64 KB.  The transposed product
+                     // K^T t of the same CG iteration then streams these tiles (sa_ktv) instead of forming K again.
+  int kstore_nj;     // 128-column blocks per row block of the store
+  long long kstore_rows;  // rows the store holds (a rounded up to 128); the odd row tile of a CTA pair lies beyond
   long long* trace;  // SAB_TRACE_PTR (developer tool): clock64 event log of CTA 0's MMA thread
   int debug;   // SAB_DEBUG bit mask, timing experiments only (results are garbage): 1 = no TMA
                // loads after the first fill, 2 = epilogue skips everything, 4 = no P V products,
@@ -578,6 +584,22 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             w[8 + c / 2] = *reinterpret_cast<const uint32_t*>(&lo);
           }
           if (!(P.debug & 8)) tmem_st_32x16(tacc + static_cast<uint32_t>(c0), w);
+          if (P.kstore != nullptr) {
+            // 16 columns = two 16-byte chunks of hi and two of lo in the row of the 128 x 128 tile they fall into
+            // (BN and the chunk origin are multiples of 16, so a group never straddles two tiles); all 128 lanes
+            // write, rows past `a` included -- they meet zeros of the converted t in sa_ktv, never stale memory
+            const long long colg = col0 + c0;
+            const int jb = static_cast<int>(colg >> 7);
+            if (jb < P.kstore_nj && grow < P.kstore_rows) {
+              const int r = static_cast<int>(grow & 127), sw = r & 7;
+              const int cc = static_cast<int>(colg & 127) >> 3;
+              uint8_t* trow = P.kstore + ((grow >> 7) * P.kstore_nj + jb) * 65536ll + r * 512;
+              *reinterpret_cast<uint4*>(trow + ((cc ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(trow + (((cc + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+              *reinterpret_cast<uint4*>(trow + (((16 + cc) ^ sw) << 4)) = make_uint4(w[8], w[9], w[10], w[11]);
+              *reinterpret_cast<uint4*>(trow + (((17 + cc) ^ sw) << 4)) = make_uint4(w[12], w[13], w[14], w[15]);
+            }
+          }
         }
       }
       if (!DENSE) tmem_wait_st();
@@ -853,8 +875,10 @@ int64_t workspace_bytes(int64_t b, int dp) {
 int launch(void* stream, int kernel, float kscale, const void* A, const float* nA, int64_t a,
            int64_t lda, const void* B, const float* nB, int64_t b, int64_t ldb, int64_t p_pad,
            const float* V, int dp, float* out, int64_t ldo, int symmetric, int mode, void* ws,
-           int64_t ws_bytes, float alpha, float gamma, int lower, const float* alpha_dev) {
+           int64_t ws_bytes, float alpha, float gamma, int lower, const float* alpha_dev, void* kstore = nullptr) {
   const bool dense = mode != MODE_KMV;
+  SAB_REQUIRE(kstore == nullptr || (mode == MODE_KMV && (reinterpret_cast<uintptr_t>(kstore) & 127) == 0),
+              "the kernel-block store needs the fused product and a 128-byte aligned buffer");
   SAB_REQUIRE(kernel >= 0 && kernel <= 3, "unknown kernel id %d", kernel);
   SAB_REQUIRE(a >= 0 && b >= 0, "negative row count");
   if (a == 0 || b == 0) return 0;
@@ -917,6 +941,9 @@ int launch(void* stream, int kernel, float kscale, const void* A, const float* n
   P.alpha_dev = alpha_dev;
   P.gamma = gamma;
   P.lower = lower;
+  P.kstore = static_cast<uint8_t*>(kstore);
+  P.kstore_nj = static_cast<int>(ceil_div(b, 128));
+  P.kstore_rows = ceil_div(a, 128) * 128;
   P.debug = env_int("SAB_DEBUG", 0);
   {
     char tp[64];
@@ -999,6 +1026,23 @@ extern "C" int sa_kmv(void* stream, int kernel, float kscale, const void* A, con
                       int64_t workspace_bytes) {
   return sab::kmv::launch(stream, kernel, kscale, A, nA, a, lda, B, nB, b, ldb, p_pad, V, dp, out, dp,
                           symmetric, sab::kmv::MODE_KMV, workspace, workspace_bytes, 0.f, 0.f, 0, nullptr);
+}
+
+extern "C" int64_t sa_kstore_bytes(int64_t a, int64_t b) {
+  if (a <= 0 || b <= 0) return -1;
+  return sab::ceil_div(a, 128) * sab::ceil_div(b, 128) * 65536ll;
+}
+
+extern "C" int sa_kmv_store(void* stream, int kernel, float kscale, const void* A, const float* nA,
+                            int64_t a, int64_t lda, const void* B, const float* nB, int64_t b, int64_t ldb,
+                            int64_t p_pad, const float* V, int dp, float* out, void* workspace,
+                            int64_t workspace_bytes, void* kstore, int64_t kstore_bytes) {
+  if (kstore == nullptr || kstore_bytes < sa_kstore_bytes(a, b)) {
+    sab::set_error("kernel-block store must hold sa_kstore_bytes(a, b) = %lld bytes", (long long)sa_kstore_bytes(a, b));
+    return 2;
+  }
+  return sab::kmv::launch(stream, kernel, kscale, A, nA, a, lda, B, nB, b, ldb, p_pad, V, dp, out, dp, 0,
+                          sab::kmv::MODE_KMV, workspace, workspace_bytes, 0.f, 0.f, 0, nullptr, kstore);
 }
 
 extern "C" int sa_kdense(void* stream, int kernel, float kscale, const void* A, const float* nA,

@@ -605,6 +605,174 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
 }
 
 // ----------------------------------------------------------------------------------------------
+// K^T t from a stored kernel block (the second half of a CG iteration's K_nM^T (K_nM z))
+// ----------------------------------------------------------------------------------------------
+// sa_kmv_store leaves k(X_blk, C) behind as packed 128 x 128 hi/lo tiles (the image above; entries carry
+// 2^14, the residual another 2^11).  out[j, :] += sum_i k(x_i, c_j) t[i, :] is then the transposed tile
+// product of the backward solve without any dependency: HBM-bound streaming of the block (4 bytes per
+// kernel entry, once) instead of forming K a second time on the tensor cores (2 p flops per entry).
+// t is converted per 128-row block like a published x (fp16 hi / lo, lo x 2^11, power-of-two block scale).
+struct KtvParams {
+  const uint8_t* tiles;   // [ni][nj] packed tiles
+  const uint8_t* that;    // [ni][xhat_bytes] converted t blocks
+  float* out;             // [b x dp], accumulated into (red.add)
+  long long b;
+  int ni, nj, dp, chunk;  // chunk = row blocks per work item
+};
+
+template <int NB8>
+__global__ void __launch_bounds__(256) that_kernel(const float* __restrict__ t, long long a, int dp,
+                                                   uint8_t* __restrict__ that) {
+  constexpr int NP = NB8 * 8;
+  constexpr int XB = xhat_bytes(NB8);
+  __shared__ float red[8];
+  const long long r0 = static_cast<long long>(blockIdx.x) * TS;
+  uint8_t* dst = that + static_cast<long long>(blockIdx.x) * XB;
+  float m = 0.f;
+  for (int idx = threadIdx.x; idx < TS * dp; idx += 256) {
+    const long long r = r0 + idx / dp;
+    if (r < a) m = fmaxf(m, fabsf(t[r * dp + idx % dp]));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  int e = 14;
+  if (m > 0.f && m < 3.0e38f) frexpf(m, &e);
+  const float sc = ldexpf(1.f, 14 - e);
+  for (int idx = threadIdx.x; idx < TS * NP; idx += 256) {
+    const int k = idx / NP, n = idx % NP;
+    const long long r = r0 + k;
+    const float v = (n < dp && r < a) ? t[r * dp + n] * sc : 0.f;
+    const __half h = __float2half_rn(v);
+    *reinterpret_cast<__half*>(dst + xoff(n, k)) = h;
+    *reinterpret_cast<__half*>(dst + NP * 256 + xoff(n, k)) = __float2half_rn((v - __half2float(h)) * 2048.f);
+  }
+  if (threadIdx.x == 0) *reinterpret_cast<float*>(dst + 2 * NP * 256) = ldexpf(1.f, e - 14);
+}
+
+struct KtvSmem {
+  unsigned long long full[NSLOT], empty[NSLOT], xfull[NXSLOT], xempty[NXSLOT];
+};
+
+template <int NB8>
+__global__ void __launch_bounds__(THREADS, 1) ktv_kernel(const KtvParams p) {
+  constexpr int NP = NB8 * 8;
+  constexpr int XB = xhat_bytes(NB8);
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* ring = smem_raw;
+  uint8_t* xring = ring + NSLOT * HALF_BYTES;
+  KtvSmem& sm = *reinterpret_cast<KtvSmem*>(xring + NXSLOT * XB);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(smem_u32(&sm.full[s]), 1);
+      mbar_init(smem_u32(&sm.empty[s]), NCONS);
+    }
+    for (int s = 0; s < NXSLOT; ++s) {
+      mbar_init(smem_u32(&sm.xfull[s]), 1);
+      mbar_init(smem_u32(&sm.xempty[s]), NCONS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  // items: (row chunk ic, column block jb), jb fastest -- the CTAs running together read the same converted
+  // t blocks (L2 resident) against different tile columns
+  const int nchunks = (p.ni + p.chunk - 1) / p.chunk;
+  const long long nitems = static_cast<long long>(nchunks) * p.nj;
+  if (warp == NCONS) {
+    int g = 0;
+    for (long long id = blockIdx.x; id < nitems; id += gridDim.x) {
+      const int ic = static_cast<int>(id / p.nj), jb = static_cast<int>(id % p.nj);
+      const int i1 = min(p.ni, (ic + 1) * p.chunk);
+      for (int ib = ic * p.chunk; ib < i1; ++ib) {
+        const uint8_t* src = p.tiles + (static_cast<long long>(ib) * p.nj + jb) * TILE_BYTES;
+#pragma unroll
+        for (int h = 0; h < 2; ++h, ++g) {
+          const int s = g % NSLOT;
+          mbar_wait(smem_u32(&sm.empty[s]), ((g / NSLOT) & 1) ^ 1);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(smem_u32(&sm.full[s]), HALF_BYTES);
+            bulk_load_1d(smem_u32(ring + s * HALF_BYTES), src + h * HALF_BYTES, HALF_BYTES, smem_u32(&sm.full[s]));
+          }
+        }
+      }
+    }
+  } else if (warp == NCONS + 1) {
+    int xg = 0;
+    for (long long id = blockIdx.x; id < nitems; id += gridDim.x) {
+      const int ic = static_cast<int>(id / p.nj);
+      const int i1 = min(p.ni, (ic + 1) * p.chunk);
+      for (int ib = ic * p.chunk; ib < i1; ++ib, ++xg) {
+        const int s = xg % NXSLOT;
+        mbar_wait(smem_u32(&sm.xempty[s]), ((xg / NXSLOT) & 1) ^ 1);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(smem_u32(&sm.xfull[s]), XB);
+          bulk_load_1d(smem_u32(xring + s * XB), p.that + static_cast<long long>(ib) * XB, XB, smem_u32(&sm.xfull[s]));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int m0 = warp * 16;
+    const uint32_t ring_a = smem_u32(ring), xring_a = smem_u32(xring);
+    int T = 0;
+    for (long long id = blockIdx.x; id < nitems; id += gridDim.x) {
+      const int ic = static_cast<int>(id / p.nj), jb = static_cast<int>(id % p.nj);
+      const int i1 = min(p.ni, (ic + 1) * p.chunk);
+      float S[NB8][4];
+#pragma unroll
+      for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) S[nb][q] = 0.f;
+      for (int ib = ic * p.chunk; ib < i1; ++ib, ++T) {
+        const int xs = T % NXSLOT;
+        mbar_wait(smem_u32(&sm.xfull[xs]), (T / NXSLOT) & 1);
+        const uint32_t xop = xring_a + xs * XB;
+        const float xinv = *reinterpret_cast<const float*>(xring + xs * XB + 2 * NP * 256);
+        float acc[NB8][4], acx[NB8][4];
+#pragma unroll
+        for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[nb][q] = acx[nb][q] = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int g = 2 * T + h, s = g % NSLOT;
+          mbar_wait(smem_u32(&sm.full[s]), (g / NSLOT) & 1);
+          mma_steps<NB8, true, 4>(ring_a + s * HALF_BYTES, xop, h * 4, m0, acc, acx);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&sm.empty[s]));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm.xempty[xs]));
+#pragma unroll
+        for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) S[nb][q] = fmaf(fmaf(acx[nb][q], 1.f / 2048.f, acc[nb][q]), xinv, S[nb][q]);
+      }
+      // entries of the stored block carry 2^14
+      const long long row = static_cast<long long>(jb) * TS + m0 + g8;
+#pragma unroll
+      for (int nb = 0; nb < NB8; ++nb) {
+        const int cc = nb * 8 + 2 * t4;
+        if (cc < p.dp) {
+          if (row < p.b) {
+            red_add_f32(p.out + row * p.dp + cc, S[nb][0] * (1.f / 16384.f));
+            red_add_f32(p.out + row * p.dp + cc + 1, S[nb][1] * (1.f / 16384.f));
+          }
+          if (row + 8 < p.b) {
+            red_add_f32(p.out + (row + 8) * p.dp + cc, S[nb][2] * (1.f / 16384.f));
+            red_add_f32(p.out + (row + 8) * p.dp + cc + 1, S[nb][3] * (1.f / 16384.f));
+          }
+        }
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // packing
 // ----------------------------------------------------------------------------------------------
 __global__ void absmax_lower_kernel(const float* __restrict__ A, long long M, long long lda, unsigned* out) {
@@ -889,4 +1057,60 @@ extern "C" int sa_trsm_solve_pair(void* stream, const void* packed_a, const void
   p.job[0] = make_job(packed_a, M, Xa, Xa, nullptr, 0.f);
   p.job[1] = make_job(packed_b, M, Xa, Xb, V, lambda);
   return solve_jobs(static_cast<cudaStream_t>(stream), p, M, dp, transpose, workspace, workspace_bytes);
+}
+
+// ---- K^T t from a stored kernel block
+extern "C" int64_t sa_ktv_workspace_bytes(int64_t a) {
+  if (a <= 0) return -1;
+  return ((a + TS - 1) / TS) * static_cast<int64_t>((xhat_bytes(4) + 127) / 128 * 128) + 256;
+}
+
+template <int NB8>
+static int ktv_launch(cudaStream_t st, const float* t, int64_t a, KtvParams p, uint8_t* that) {
+  that_kernel<NB8><<<p.ni, 256, 0, st>>>(t, a, p.dp, that);
+  SAB_CHECK_CUDA(cudaGetLastError());
+  const int smem = NSLOT * HALF_BYTES + NXSLOT * xhat_bytes(NB8) + static_cast<int>(sizeof(KtvSmem));
+  auto kern = ktv_kernel<NB8>;
+  SAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const long long nitems = static_cast<long long>((p.ni + p.chunk - 1) / p.chunk) * p.nj;
+  const int grid = static_cast<int>(nitems < sm_count() ? nitems : sm_count());
+  kern<<<grid, THREADS, smem, st>>>(p);
+  SAB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sa_ktv(void* stream, const void* kstore, int64_t a, int64_t b, const float* t, int dp, float* out,
+                      void* workspace, int64_t workspace_bytes) {
+  SAB_REQUIRE(kstore != nullptr && t != nullptr && out != nullptr && a > 0 && b > 0, "bad operands");
+  SAB_REQUIRE((reinterpret_cast<uintptr_t>(kstore) & 127) == 0, "the kernel-block store must be 128-byte aligned");
+  SAB_REQUIRE(dp >= 4 && dp <= 32 && dp % 4 == 0, "dp must be a multiple of 4 in [4, 32], got %d", dp);
+  SAB_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 127) == 0 &&
+                  workspace_bytes >= sa_ktv_workspace_bytes(a),
+              "workspace must be 128-byte aligned and hold sa_ktv_workspace_bytes(a) = %lld bytes",
+              (long long)sa_ktv_workspace_bytes(a));
+  KtvParams p;
+  p.tiles = static_cast<const uint8_t*>(kstore);
+  p.that = static_cast<const uint8_t*>(workspace);
+  p.out = out;
+  p.b = b;
+  p.ni = static_cast<int>((a + TS - 1) / TS);
+  p.nj = static_cast<int>((b + TS - 1) / TS);
+  p.dp = dp;
+  // row blocks per item: long enough to amortise the per-item atomics, short enough to balance the SMs
+  int chunk = option_int("SAB_KTV_CHUNK", 0);
+  if (chunk <= 0) {
+    const long long want_items = 8ll * sm_count();
+    chunk = static_cast<int>((static_cast<long long>(p.ni) * p.nj + want_items - 1) / want_items);
+    if (chunk < 8) chunk = 8;
+    if (chunk > 128) chunk = 128;
+  }
+  p.chunk = chunk < p.ni ? chunk : p.ni;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* that = static_cast<uint8_t*>(workspace);
+  switch ((dp + 7) / 8) {
+    case 1: return ktv_launch<1>(st, t, a, p, that);
+    case 2: return ktv_launch<2>(st, t, a, p, that);
+    case 3: return ktv_launch<3>(st, t, a, p, that);
+    default: return ktv_launch<4>(st, t, a, p, that);
+  }
 }

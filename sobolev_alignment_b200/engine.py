@@ -227,8 +227,14 @@ class CudaOps:
         main.wait_stream(side)
 
     # ------------------------------------------------------------------ numerical operations
-    def kmv(self, spec: KernelSpec, frame: Frame, A, B, V, out, symmetric=False):
-        return nat.kmv(spec.kid, spec.kscale(frame.gscale), A, B, V, out, symmetric)
+    def kmv(self, spec: KernelSpec, frame: Frame, A, B, V, out, symmetric=False, kstore=None):
+        return nat.kmv(spec.kid, spec.kscale(frame.gscale), A, B, V, out, symmetric, kstore)
+
+    ktv = staticmethod(nat.ktv)
+    kstore_bytes = staticmethod(nat.kstore_bytes)
+
+    def free_bytes(self) -> int:
+        return int(torch.cuda.mem_get_info(self.device)[0])
 
     def kdense(self, spec: KernelSpec, frame: Frame, A, B, out, symmetric=False):
         return nat.kdense(spec.kid, spec.kscale(frame.gscale), A, B, out, symmetric)

@@ -106,10 +106,13 @@ class Falkon:
         n_local = X.shape[0]
         if comm.enabled and comm.world > 1:
             centres, n_total = self._gather_centres(X, comm, ops)
+            t_gather = time.perf_counter() - t0
         else:
+            t_gather = 0.0
             idx = self._select_centres(n_local)
             centres = X.rows(idx) if deferred else X[torch.from_numpy(idx).to(X.device)]
             n_total = n_local
+            t_gather = time.perf_counter() - t0
         # Row-sharded fit from host inputs: `ny_points_` has to be a host tensor again (anchors() contract).
         # Its 600 MB read-back (C3) runs on a helper thread / side stream while the solver works.
         # results live where the inputs live; deferred rows always sit on the device, so Y decides for them
@@ -119,17 +122,23 @@ class Falkon:
             fetch = _HostFetch(centres)
         solver = FalkonSolver(ops, self.kernel.spec(), self.penalty, self.maxiter, pc_eps=opt.pc_eps(),
                               cg_eps=float(opt.cg_epsilon_32), cg_tol=float(opt.cg_tolerance),
-                              full_grad_every=int(opt.cg_full_gradient_every), comm=comm)
+                              full_grad_every=int(opt.cg_full_gradient_every), comm=comm,
+                              kernel_blocks="recompute" if opt.never_store_kernel else str(opt.kernel_blocks),
+                              kstore_budget=int(opt.kstore_budget))
         alpha = solver.fit(X, Y, centres, n_total=n_total)
         self.solver_stats_ = {"times": dict(solver.times), "residuals": list(solver.residuals),
                               "n_iter": solver.n_iter_, "n_kmv": solver.n_kmv_, "n_total": n_total}
         solver.release()
+        t1 = time.perf_counter()
         self.alpha_ = alpha.to(Y.dtype) if on_device else alpha.to(Y.dtype).cpu()
         if fetch is not None:
             self.ny_points_ = fetch.result()
         else:
             self.ny_points_ = centres if centres.is_cuda == on_device else (centres.cuda() if on_device else centres.cpu())
         self.fit_times_ = [time.perf_counter() - t0]
+        # host-side wall clock outside the solver: centre selection / exchange, and the read-back of the results
+        self.solver_stats_["times"].update({"select_centres": t_gather, "read_back": time.perf_counter() - t1,
+                                            "estimator_wall": self.fit_times_[0]})
         self._predictor = None
         if self.error_fn is not None and Xts is not None and Yts is not None:
             err = self.error_fn(Yts, self.predict(Xts))

@@ -53,6 +53,9 @@ _DEFAULTS = {
     "center_seed": None,       # seed of the centre draw when Falkon(seed=None); required if row_sharded
     "stage_rows": 65536,       # rows per pinned host->device staging chunk
     "device": None,            # cuda device index; default: current device
+    "kernel_blocks": "recompute",  # "store": form K once per CG product pair through a transient row-block scratch
+                                   # (design B; ignored when never_store_kernel=True)
+    "kstore_budget": 24 << 30,     # bytes of that scratch
 }
 
 

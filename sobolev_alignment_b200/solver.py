@@ -190,7 +190,18 @@ class _CgColumns:
 
 class FalkonSolver:
     def __init__(self, ops, spec: KernelSpec, penalty, maxiter: int = 20, pc_eps: float = 1e-5,
-                 cg_eps: float = 1e-7, cg_tol: float = 1e-7, full_grad_every: int = 10, comm: Comm | None = None):
+                 cg_eps: float = 1e-7, cg_tol: float = 1e-7, full_grad_every: int = 10, comm: Comm | None = None,
+                 kernel_blocks: str = "recompute", kstore_budget: int = 24 << 30):
+        """
+        kernel_blocks: how K_nM^T (K_nM z) is formed.  "recompute" (default, the north-star design): the fused
+        kernel runs twice, K_nM never exists in HBM.  "store": K is formed ONCE per product pair -- row block by
+        row block the forward product also leaves the block behind as packed fp16 hi/lo tiles in a transient
+        scratch of at most `kstore_budget` bytes, and K^T t streams it back (HBM-bound) -- SURVEY section 7,
+        design (B); falkon's `never_store_kernel=False`.
+        """
+        if kernel_blocks not in ("recompute", "store"):
+            raise ValueError("kernel_blocks must be 'recompute' or 'store'")
+        self.kernel_blocks, self.kstore_budget = kernel_blocks, int(kstore_budget)
         self.ops, self.spec = ops, spec
         self.penalties = [float(x) for x in (penalty if isinstance(penalty, (list, tuple)) else [penalty])]
         self.penalty, self.maxiter = self.penalties[0], int(maxiter)
@@ -207,12 +218,35 @@ class FalkonSolver:
         """out[:M] = sum over local rows of K_g^T (K_g Z[:M]), all-reduced over ranks (any <= 32 columns)."""
         ops, M = self.ops, self.M
         self.t_buf.zero_()
-        ops.kmv(self.spec, self.frame, self.Xprep, self.Cprep, Z[:M], self.t_buf)
         out.zero_()
-        ops.kmv(self.spec, self.frame, self.Cprep, self.Xprep, self.t_buf, out[:M])
-        self.n_kmv_ += 2
+        if self.kernel_blocks == "store" and hasattr(ops, "ktv"):
+            for r0, r1, Xb in self._row_blocks():
+                tb = self.t_buf[r0:r1]
+                ops.kmv(self.spec, self.frame, Xb, self.Cprep, Z[:M], tb, kstore=self.kstore)
+                ops.ktv(self.kstore, r1 - r0, M, tb, out[:M])
+            self.n_kmv_ += 1
+        else:
+            ops.kmv(self.spec, self.frame, self.Xprep, self.Cprep, Z[:M], self.t_buf)
+            ops.kmv(self.spec, self.frame, self.Cprep, self.Xprep, self.t_buf, out[:M])
+            self.n_kmv_ += 2
         self.comm.all_reduce(out)
         return out
+
+    def _row_blocks(self):
+        """Row blocks of the prepared rows whose kernel block fits the scratch: whole waves of CTA pairs (148 x 128 rows)."""
+        if getattr(self, "_blocks", None) is None:
+            ops, n, M = self.ops, self.Xprep.n, self.M
+            wave = getattr(ops, "wave_rows", 148 * 128)
+            per_wave = ops.kstore_bytes(wave, M)
+            budget = min(self.kstore_budget, int(0.5 * ops.free_bytes()))
+            rows = max(1, budget // per_wave) * wave
+            rows = min(rows, (n + 127) // 128 * 128)
+            self.kstore = ops.zeros(ops.kstore_bytes(min(rows, n), M), dtype=torch.uint8)
+            self._blocks = []
+            for r0 in range(0, n, rows):
+                r1 = min(n, r0 + rows)
+                self._blocks.append((r0, r1, self.Xprep.rows(r0, r1)))
+        return self._blocks
 
     def _bhb(self, states, src, dst):
         """
@@ -433,7 +467,7 @@ class FalkonSolver:
 
     # ------------------------------------------------------------------ release
     def release(self):
-        for name in ("pre", "Xprep", "t_buf", "Zw", "Ww"):
+        for name in ("pre", "Xprep", "t_buf", "Zw", "Ww", "kstore", "_blocks"):
             if hasattr(self, name):
                 delattr(self, name)
 

@@ -19,6 +19,9 @@ class _Rows:
     def __init__(self, data):
         self.data, self.n, self.p = data, data.shape[0], data.shape[1]
 
+    def rows(self, r0, r1):
+        return _Rows(self.data[r0:r1])
+
 
 class _CgScratch:
     """Same contract as _native.CgScratch: residual history, stop flag, late polls."""
@@ -71,9 +74,23 @@ class CpuOps:
         fam, nu = _FAMILY[spec.family]
         return fo.kernel_matrix(A.data, B.data, fam, spec.sigma, nu, direct=False)
 
-    def kmv(self, spec, frame, A, B, V, out, symmetric=False):
-        out += self._k(spec, A, B) @ V
+    def kmv(self, spec, frame, A, B, V, out, symmetric=False, kstore=None):
+        K = self._k(spec, A, B)
+        out += K @ V
+        if kstore is not None:
+            self._stored = K            # the CUDA engine leaves packed fp16 hi/lo tiles in `kstore`
         return out
+
+    def ktv(self, kstore, a, b, t, out):
+        assert self._stored.shape == (a, b)
+        out += self._stored.T @ t
+        return out
+
+    def kstore_bytes(self, a, b):
+        return ((a + 127) // 128) * ((b + 127) // 128) * 65536
+
+    def free_bytes(self):
+        return 1 << 40
 
     def kdense(self, spec, frame, A, B, out, symmetric=False):
         out[: A.n, : B.n] = self._k(spec, A, B)

@@ -279,6 +279,24 @@ def test_grid_matches_independent_fits():
         assert relerr(clf.transform(Xv), pred_ref) < PRED_TOL, (nu, lam)
 
 
+def test_fit_with_stored_kernel_blocks():
+    """FalkonOptions(kernel_blocks='store'): K formed once per CG product pair (several row blocks); same golden."""
+    g = load_golden("config1")
+    Xall = syn.log_counts_numpy(2050, 500, seed=0)
+    Yall = syn.targets_numpy(Xall, 10, seed=1, linear=True)
+    X, Xv, Y = torch.from_numpy(Xall[:2000]), torch.from_numpy(Xall[2000:]), torch.from_numpy(Yall[:2000])
+    clf = KRRApprox(method="falkon", kernel="laplacian", kernel_params={"sigma": 10.0}, penalization=1e-3, M=500,
+                    falkon_options={"kernel_blocks": "store", "kstore_budget": 1})      # budget of one wave: 1 block here
+    _fit_with_centres(clf, X, Y, g["idx"])
+    assert clf.ridge_clf_.solver_stats_["n_kmv"] == 1 + 21
+    assert relerr(clf.transform(Xv), g["lap_pred"]) < PRED_TOL
+    ref = KRRApprox(method="falkon", kernel="laplacian", kernel_params={"sigma": 10.0}, penalization=1e-3, M=500,
+                    falkon_options={"never_store_kernel": True, "kernel_blocks": "store"})   # upstream switch wins
+    _fit_with_centres(ref, X, Y, g["idx"])
+    assert ref.ridge_clf_.solver_stats_["n_kmv"] == 43
+    assert relerr(clf.transform(Xv), ref.transform(Xv).double()) < 2e-4
+
+
 # ---------------------------------------------------------------------------- row-sharded fit on the real engine
 def _sharded_rank_main(rank, world, port, out_dir):
     import os

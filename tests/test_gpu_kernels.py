@@ -390,6 +390,41 @@ def test_kernel_object_is_callable_like_falkon(cuda_ops):
     assert relerr(k.dmmv(A, B, v, w), Kd.T @ (Kd @ v.double() + w.double())) < 3e-4
 
 
+@pytest.mark.parametrize("family,okernel,nu", FAMILIES)
+@pytest.mark.parametrize("a,b,p,d", [(128, 128, 64, 4), (300, 500, 100, 7), (2000, 777, 333, 20), (5000, 1500, 200, 32)])
+def test_stored_block_product_matches_oracle(cuda_ops, family, okernel, nu, a, b, p, d):
+    """
+    sa_kmv_store + sa_ktv: K(A, B) V with the kernel block left behind as packed fp16 hi/lo tiles, then
+    K(A, B)^T t streamed from it -- both against the float64 oracle (1e-4, the K_nM v budget), and the stored
+    route against the recomputing transposed product.
+    """
+    from sobolev_alignment_b200 import _native as nat
+    from sobolev_alignment_b200.engine import KernelSpec, pad_cols
+
+    g = torch.Generator().manual_seed(a + 3 * b + p)
+    A = torch.from_numpy(syn.log_counts_numpy(a, p, seed=a + b))
+    B = torch.from_numpy(syn.log_counts_numpy(b, p, seed=a + b + 1))
+    V, T = torch.randn(b, d, generator=g), torch.randn(a, d, generator=g)
+    spec = KernelSpec(family, 7.0)
+    frame = cuda_ops.make_frame(B.cuda(), spec)
+    Ap, Bp = cuda_ops.prepare(A, frame), cuda_ops.prepare(B, frame)
+    dp = pad_cols(d)
+    Vd, Td = cuda_ops.zeros(b, dp), cuda_ops.zeros(a, dp)
+    Vd[:, :d], Td[:, :d] = V.cuda(), T.cuda()
+    store = torch.full((nat.kstore_bytes(a, b),), 0xFF, dtype=torch.uint8, device="cuda")   # NaN patterns if unwritten
+    out = cuda_ops.zeros(a, dp)
+    cuda_ops.kmv(spec, frame, Ap, Bp, Vd, out, kstore=store)
+    Kd = fo.kernel_matrix(A, B, okernel, 7.0, nu)
+    assert relerr(out[:, :d], Kd @ V.double()) < 1e-4
+    wt = cuda_ops.zeros(b, dp)
+    cuda_ops.ktv(store, a, b, Td, wt)
+    assert relerr(wt[:, :d], Kd.T @ T.double()) < 1e-4
+    again = cuda_ops.zeros(b, dp)
+    cuda_ops.kmv(spec, frame, Bp, Ap, Td, again)
+    assert relerr(wt[:, :d], again[:, :d].double()) < 1e-4
+    assert float(wt[:, d:].abs().max()) == 0.0 if dp > d else True
+
+
 # ---------------------------------------------------------------------------- preconditioner algebra
 @pytest.mark.parametrize("M,dp,nb", [(128, 4, None), (384, 12, 128), (1024, 20, None), (2048, 32, 256), (2048, 20, "simt")])
 def test_cholesky_ltl_trsm(cuda_ops, M, dp, nb, sab_option):

@@ -452,3 +452,20 @@ def test_grid_shares_preconditioner_and_cg_launches_stand_in_engine():
         assert relerr(clf.sample_weights_, ref) < 1e-6, (nu, lam)
         assert clf.penalization == lam and clf.kernel_params["nu"] == nu
         assert torch.equal(clf.anchors(), C)
+
+
+def test_stored_kernel_blocks_solver_path_stand_in_engine():
+    """kernel_blocks='store' (K formed once per product pair, row block by row block) == the recompute path."""
+    X, Xv, W, Y, Yv = krr_test_data(seed=15, n=700, p=12, d=3, n_valid=10)
+    idx = np.sort(np.random.default_rng(1).choice(700, size=80, replace=False))
+    outs = {}
+    for mode in ("recompute", "store"):
+        ops = CpuOps()
+        ops.kstore_bytes = lambda a, b: ((a + 127) // 128) * 1000       # tiny budget below: 3 row blocks of 256 rows
+        ops.wave_rows = 256
+        solver = FalkonSolver(ops, KernelSpec("laplacian", 6.0), 1e-4, kernel_blocks=mode, kstore_budget=2000)
+        outs[mode] = solver.fit(X, Y, X[idx])
+        if mode == "store":
+            assert len(solver._blocks) > 1
+            assert solver.n_kmv_ == 1 + 21        # rhs + one K formation per product pair (43 launches when recomputed)
+    assert relerr(outs["store"], outs["recompute"]) < 1e-10
