@@ -462,8 +462,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_fit(Xin, Yin, through_krr_approx=False):
-        opts = dict(row_sharded=world > 1, center_seed=11)
+    def one_fit(Xin, Yin, through_krr_approx=False, **extra):
+        opts = dict(row_sharded=world > 1, center_seed=11, **extra)
         if through_krr_approx:
             clf = KRRApprox(method="falkon", kernel=kernel, kernel_params=kparams, M=M, penalization=lam,
                             maxiter=MAXITER, falkon_options=opts)
@@ -505,6 +505,24 @@ def main():
     kmv_flops, kmv_s, kmv_n = nat.STATS.kmv_summary()
     trsm_bytes, trsm_s, trsm_n = nat.STATS.trsm_summary()
     stats = est.solver_stats_
+
+    # ---------------- secondary: the same fit with stored kernel blocks (design B; K formed once per product pair)
+    stored = None
+    if not args.no_extras and cfg_name == "C3":
+        def _stored():
+            one_fit(X, Y, kernel_blocks="store")
+            nat.STATS.reset()
+            nat.STATS.time_kmv = True
+            ms_b, _, est_b = timed(lambda: one_fit(X, Y, kernel_blocks="store"), 2)
+            nat.STATS.time_kmv = False
+            fl, ks, kn = nat.STATS.kmv_summary()
+            by, bs, bn = nat.STATS.ktv_summary()
+            return {"fit_s": ms_b / 1e3, "steps": 2, "kmv_tflops": fl / ks / 1e12 if ks else None, "kmv_launches_timed": kn,
+                    "ktv_gbs": by / bs / 1e9 if bs else None, "ktv_seconds_per_fit": bs / 2, "kmv_seconds_per_fit": ks / 2,
+                    "phases_s": est_b.solver_stats_["times"], "final_residual": est_b.solver_stats_["residuals"][-1],
+                    "what": "FalkonOptions(kernel_blocks='store'): K formed once per CG product pair, row blocks left behind as "
+                            "packed fp16 hi/lo tiles (transient scratch <= 24 GB), K^T t streamed back (sa_ktv)"}
+        stored = _guard(_stored)
 
     # ---------------- end-to-end arm: pinned host inputs through KRRApprox.fit
     e2e = None
@@ -569,6 +587,8 @@ def main():
         line["transform"] = extras_host["transform"]
     if c4 is not None:
         line["c4"] = c4
+    if stored is not None:
+        line["stored_kernel_blocks"] = stored
     if not args.no_extras and world == 1 and cfg_name == "C3":
         torch.cuda.empty_cache()
         line["c2"] = _guard(leg_c2, dev, args)

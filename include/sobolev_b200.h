@@ -168,6 +168,11 @@ int sa_potrf_split(void* stream, int64_t M, const float* panel, int64_t ldp, int
                    void* workspace, int64_t workspace_bytes);
 int sa_potrf_update(void* stream, float* A, int64_t M, int64_t lda, int kend, int c0, int c1,
                     const float* panel, int64_t ldp, int W, void* workspace, int64_t workspace_bytes);
+/* sa_potrf_update for every outer panel (nb blocks wide) a rank owns in one call: panels first, first + stride, ...
+ * except `skip` (-1: none). */
+int sa_potrf_update_cyclic(void* stream, float* A, int64_t M, int64_t lda, int kend, int nb, int first, int stride,
+                           int skip, const float* panel, int64_t ldp, int W, void* workspace,
+                           int64_t workspace_bytes);
 
 /* G(lower) = alpha * L^T L + beta * I   (falkon `lauum` + `mul_triang` + add-diagonal [ext]);
  * same workspace contract as sa_potrf. */

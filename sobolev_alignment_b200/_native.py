@@ -98,6 +98,8 @@ _SIGNATURES = {
     "sa_potrf_split": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64]),
     "sa_potrf_update": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_int,
                                 c_void_p, c_int64]),
+    "sa_potrf_update_cyclic": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                       c_int64, c_int, c_void_p, c_int64]),
     "sa_ltl": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p,
                        c_int64]),
     "sa_ltl_part": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p,
@@ -428,6 +430,16 @@ def potrf_update(A: torch.Tensor, kend: int, c0: int, c1: int, panel: torch.Tens
     _call(load().sa_potrf_update, A.device, A.data_ptr(), A.shape[0], A.stride(0), int(kend), int(c0), int(c1),
           panel.data_ptr(), panel.stride(0), int(W), ws.data_ptr(), ws.numel())
     STATS.launches += 3
+
+
+def potrf_update_cyclic(A: torch.Tensor, kend: int, nb: int, first: int, stride: int, skip: int, panel: torch.Tensor,
+                        W: int):
+    """potrf_update for every outer panel first, first + stride, ... (except `skip`) in one library call."""
+    ws = _linalg_workspace(A.device, A.shape[0])
+    _call(load().sa_potrf_update_cyclic, A.device, A.data_ptr(), A.shape[0], A.stride(0), int(kend), int(nb), int(first),
+          int(stride), int(skip), panel.data_ptr(), panel.stride(0), int(W), ws.data_ptr(), ws.numel())
+    npan = (A.shape[0] // TILE + nb - 1) // nb
+    STATS.launches += 3 * max(0, (npan - first + stride - 1) // stride)
 
 
 def ltl(L: torch.Tensor, G: torch.Tensor, alpha: float, beta: float, part: int = 0, nparts: int = 1):

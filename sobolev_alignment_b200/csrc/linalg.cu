@@ -690,6 +690,28 @@ extern "C" int sa_potrf_update(void* stream, float* A, int64_t M, int64_t lda, i
   return potrf_update(stream, A, lda, nblk, kend, c0, c1, panel, ldp, W, carve(workspace, M));
 }
 
+// All the outer panels one rank owns in ONE call (the per-panel Python round trip -- ~40 us of ctypes per update --
+// was what bounded the distributed factorisation): panels first, first + stride, ... (outer-panel indices, each
+// `nb` blocks wide) except `skip` (the look-ahead panel, already brought up to date).
+extern "C" int sa_potrf_update_cyclic(void* stream, float* A, int64_t M, int64_t lda, int kend, int nb, int first,
+                                      int stride, int skip, const float* panel, int64_t ldp, int W, void* workspace,
+                                      int64_t workspace_bytes) {
+  SAB_REQUIRE_MAT(M, lda, A);
+  const int nblk = static_cast<int>(M / TS);
+  SAB_REQUIRE(panel != nullptr && 0 < kend && kend <= nblk && nb > 0 && nb <= outer_blocks() && first >= 0 && stride > 0 &&
+                  W > 0 && W % TS == 0 && W <= outer_blocks() * TS && ldp >= W,
+              "bad cyclic update: kend=%d nb=%d first=%d stride=%d W=%d", kend, nb, first, stride, W);
+  SAB_REQUIRE_WS(M, workspace, workspace_bytes);
+  const LinalgWs w = carve(workspace, M);
+  for (int j = first; j * nb < nblk; j += stride) {
+    if (j == skip) continue;
+    const int c0 = j * nb, c1 = c0 + nb < nblk ? c0 + nb : nblk;
+    SAB_REQUIRE(c0 >= kend, "panel %d starts before the trailing matrix (block %d)", j, kend);
+    if (int rc = potrf_update(stream, A, lda, nblk, kend, c0, c1, panel, ldp, W, w)) return rc;
+  }
+  return 0;
+}
+
 extern "C" int sa_ltl_part(void* stream, const float* L, int64_t M, int64_t ldl, float* G, int64_t ldg,
                            float alpha, float beta, void* workspace, int64_t workspace_bytes, int part,
                            int nparts) {

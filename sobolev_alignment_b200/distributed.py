@@ -79,13 +79,13 @@ def potrf(ops, A: torch.Tensor, invdiag: torch.Tensor, info: torch.Tensor, comm)
             break
         below = pv[W:]                                # rows under the panel's own diagonal blocks
         ops.potrf_split(Mp, below, W)
-        mine = [jj for jj in range(j + 1, npan) if jj % R == me]
-        if mine and mine[0] == j + 1:
+        ahead = (j + 1) % R == me
+        if ahead:
             c0, c1 = span(j + 1)
             ops.potrf_update(A, kend, c0, c1, below, W)
             factor_and_pack(j + 1)
-            mine = mine[1:]
         handle = comm.broadcast_async(payload(j + 1)[0], (j + 1) % R)
-        for jj in mine:
-            c0, c1 = span(jj)
-            ops.potrf_update(A, kend, c0, c1, below, W)
+        # the rest of this rank's share: outer panels first, first + R, ... beyond j + 1 (one library call)
+        first = j + 1 + ((me - (j + 1)) % R)
+        if first < npan:
+            ops.potrf_update_cyclic(A, kend, nb, first, R, j + 1 if ahead else -1, below, W)

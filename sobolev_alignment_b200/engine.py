@@ -245,6 +245,7 @@ class CudaOps:
     potrf_panel = staticmethod(nat.potrf_panel)
     potrf_split = staticmethod(nat.potrf_split)
     potrf_update = staticmethod(nat.potrf_update)
+    potrf_update_cyclic = staticmethod(nat.potrf_update_cyclic)
     ltl = staticmethod(nat.ltl)
     add_diag = staticmethod(nat.add_diag)
     trsm_pack = staticmethod(nat.trsm_pack)

@@ -123,6 +123,12 @@ class CpuOps:
         P = panel[off:]
         A[c0 * 128:, c0 * 128: c1 * 128] -= P @ P[:ncols].T
 
+    def potrf_update_cyclic(self, A, kend, nb, first, stride, skip, panel, W):
+        nblk = A.shape[0] // 128
+        for j in range(first, (nblk + nb - 1) // nb, stride):
+            if j != skip:
+                self.potrf_update(A, kend, j * nb, min(nblk, j * nb + nb), panel, W)
+
     def ltl(self, L, G, alpha, beta):
         Lt = torch.tril(L)
         G.copy_(alpha * (Lt.T @ Lt) + beta * torch.eye(L.shape[0], dtype=L.dtype))

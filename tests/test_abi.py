@@ -20,7 +20,7 @@ def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
     for s in ("sa_prep", "sa_prep_log", "sa_colstats", "sa_transform_rows", "sa_kmv", "sa_kmv_workspace_bytes", "sa_kstore_bytes", "sa_kmv_store",
               "sa_ktv_workspace_bytes", "sa_ktv", "sa_kdense", "sa_linalg_workspace_bytes", "sa_potrf", "sa_potrf_outer_blocks", "sa_potrf_begin", "sa_potrf_panel", "sa_potrf_split",
-              "sa_potrf_update", "sa_ltl", "sa_ltl_part", "sa_trsm_workspace_bytes", "sa_trsm_packed_bytes", "sa_trsm_pack_workspace_bytes", "sa_trsm_pack",
+              "sa_potrf_update", "sa_potrf_update_cyclic", "sa_ltl", "sa_ltl_part", "sa_trsm_workspace_bytes", "sa_trsm_packed_bytes", "sa_trsm_pack_workspace_bytes", "sa_trsm_pack",
               "sa_trsm_solve", "sa_trsm_solve_pair", "sa_set_option", "sa_cg_workspace_bytes", "sa_coldot", "sa_cg_update",
               "sa_cg_direction", "sa_axpby", "sa_add_diag", "sa_last_error", "sa_version", "sa_device_info"):
         assert s in syms
