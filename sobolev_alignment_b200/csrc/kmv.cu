@@ -594,10 +594,19 @@ kmv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
               const int r = static_cast<int>(grow & 127), sw = r & 7;
               const int cc = static_cast<int>(colg & 127) >> 3;
               uint8_t* trow = P.kstore + ((grow >> 7) * P.kstore_nj + jb) * 65536ll + r * 512;
-              *reinterpret_cast<uint4*>(trow + ((cc ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-              *reinterpret_cast<uint4*>(trow + (((cc + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
-              *reinterpret_cast<uint4*>(trow + (((16 + cc) ^ sw) << 4)) = make_uint4(w[8], w[9], w[10], w[11]);
-              *reinterpret_cast<uint4*>(trow + (((17 + cc) ^ sw) << 4)) = make_uint4(w[12], w[13], w[14], w[15]);
+              // cc is even, so the two chunks of a half (hi or lo) are the two halves of ONE aligned 32-byte sector
+              // (the swizzle only decides their order): one 256-bit store each instead of two partial-sector writes
+              const bool swap = (sw & 1) != 0;
+              uint32_t lo8[8], hi8[8];   // (register selects: no dynamic indexing of w)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                hi8[q] = swap ? w[4 + q] : w[q];
+                hi8[4 + q] = swap ? w[q] : w[4 + q];
+                lo8[q] = swap ? w[12 + q] : w[8 + q];
+                lo8[4 + q] = swap ? w[8 + q] : w[12 + q];
+              }
+              st_global_v8(trow + (((cc ^ sw) & ~1) << 4), hi8, hi8 + 4);
+              st_global_v8(trow + ((((16 + cc) ^ sw) & ~1) << 4), lo8, lo8 + 4);
             }
           }
         }

@@ -401,6 +401,12 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 __device__ __forceinline__ void prefetch_l2(const void* addr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
 }
+// 256-bit global store (sm_100+): 32 bytes = one full sector from one thread
+__device__ __forceinline__ void st_global_v8(void* addr, const uint32_t* a, const uint32_t* b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(addr), "r"(a[0]), "r"(a[1]), "r"(a[2]),
+               "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3])
+               : "memory");
+}
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }

@@ -90,7 +90,8 @@ class CudaOps:
         """fp32 contiguous copy on the device (no-op when already there)."""
         if t.is_cuda:
             return t.to(device=self.device, dtype=torch.float32).contiguous()
-        return t.to(torch.float32).contiguous().to(self.device, non_blocking=False)
+        t = t.to(torch.float32).contiguous()
+        return t.to(self.device, non_blocking=t.is_pinned())     # pinned source: stream-ordered, no host wait
 
     def to_host(self, t: torch.Tensor) -> torch.Tensor:
         return t.detach().to("cpu")
@@ -133,6 +134,12 @@ class CudaOps:
         for f in futs:
             f.result()
 
+    @staticmethod
+    def stages_without_host_work(X) -> bool:
+        """True when staging X is enqueue-only (pinned, float32, contiguous host rows): no copy through our pinned buffers."""
+        return (torch.is_tensor(X) and not X.is_cuda and X.dtype == torch.float32 and X.dim() == 2 and X.is_contiguous()
+                and X.is_pinned())
+
     def alloc_prepared(self, n: int, p: int) -> nat.Prepared:
         return nat.alloc_prepared(n, p, self.device)
 
@@ -155,6 +162,16 @@ class CudaOps:
         if n == 0:
             return out
         rows = max(1, min(self.stage_rows, n))
+        if self.stages_without_host_work(X):
+            # pinned fp32 rows: H2D straight from the caller's buffer; everything is ordered by the stream (two
+            # device chunk buffers reused in stream order), the host only enqueues
+            dev_bufs = [torch.empty(rows, p, dtype=torch.float32, device=self.device) for _ in range(min(2, -(-n // rows)))]
+            for i, s in enumerate(range(0, n, rows)):
+                e = min(n, s + rows)
+                buf = dev_bufs[i & 1][: e - s]
+                buf.copy_(X[s:e], non_blocking=True)
+                nat.prep(buf, frame.shift, frame.scale, frame.gscale, out=out, row_offset=s)
+            return out
         if self._pinned is None or self._pinned[0].shape[1] != p or self._pinned[0].shape[0] < rows:
             for ev in self._pinned_events:
                 if ev is not None:

@@ -312,12 +312,17 @@ class FalkonSolver:
                 except BaseException as exc:  # noqa: BLE001 - re-raised on the calling thread
                     staged["error"] = exc
 
-            helper = threading.Thread(target=_stage, name="sobolev-b200-staging")
-            helper.start()
+            helper = None
+            if getattr(ops, "stages_without_host_work", lambda _x: False)(X):
+                _stage()        # pinned rows: enqueue-only, done before the preconditioner's launches pile up
+            else:
+                helper = threading.Thread(target=_stage, name="sobolev-b200-staging")
+                helper.start()
         self.pre = pre = Preconditioner(ops, self.spec, self.frame, self.Cprep, self.penalties, self.pc_eps, self.comm)
         if overlap:
             ev[1].record(main)
-            helper.join()
+            if helper is not None:
+                helper.join()
             if "error" in staged:
                 raise staged["error"]
             self.Xprep, Yfull = staged["X"], staged["Y"]

@@ -39,8 +39,8 @@ t_tr = timed(lambda: nat.kmv(1, 0.1, PB, PA, t, w))
 t_st = timed(lambda: nat.kmv(1, 0.1, PA, PB, Z, t, kstore=store))
 t_ktv = timed(lambda: nat.ktv(store, a, b, t, w))
 print(f"a={a} b={b} p={p} d={d}: kmv fwd {t_fwd:.2f} ms ({fl / t_fwd / 1e9:.0f} TFLOP/s), kmv transposed {t_tr:.2f} ms "
-      f"({fl / t_tr / 1e9:.0f}), kmv fwd + store {t_st:.2f} ms ({fl / t_st / 1e9:.0f} TFLOP/s, {4.0 * a * b / t_st / 1e9:.0f} GB/s "
-      f"of stores), ktv {t_ktv:.2f} ms ({4.0 * a * b / t_ktv / 1e9:.0f} GB/s); pair: {t_fwd + t_tr:.2f} -> {t_st + t_ktv:.2f} ms")
+      f"({fl / t_tr / 1e9:.0f}), kmv fwd + store {t_st:.2f} ms ({fl / t_st / 1e9:.0f} TFLOP/s, {4.0 * a * b / t_st / 1e6:.0f} GB/s "
+      f"of stores), ktv {t_ktv:.2f} ms ({4.0 * a * b / t_ktv / 1e6:.0f} GB/s); pair: {t_fwd + t_tr:.2f} -> {t_st + t_ktv:.2f} ms")
 for ch in (8, 16, 32, 64):
     nat.set_option("SAB_KTV_CHUNK", ch)
     print(f"  SAB_KTV_CHUNK={ch}: ktv {timed(lambda: nat.ktv(store, a, b, t, w)):.2f} ms")
