@@ -334,6 +334,28 @@ def leg_c5(dev):
             "workload": f"two KRRApprox Falkon-path fits (n={n}, p={p}, M={M}, d={d}, laplacian sigma 10) + M_X/M_Y/M_XY + SVD"}
 
 
+def leg_grid(dev, single_fit_s):
+    """
+    The model-selection grid of krr_model_selection.py (4 nu x 11 penalizations, :24-52,260-266) at config-2 size:
+    KRRGrid (operands prepared once, T per nu, A per lambda, multi-lambda CG) against 44 independent fits.
+    """
+    from sobolev_alignment_b200 import synthetic as syn
+    from sobolev_alignment_b200.model_selection import KRRGrid
+
+    n, p, M, d, kernel, kparams, lam = WORKLOADS["C2"]
+    X = syn.log_counts_torch(n, p, seed=2000, device=dev)
+    Y = syn.targets_torch(X, d, seed=7)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    grid = KRRGrid(X, Y, M=M, sigma=10.0, kernel="matern", center_seed=11)
+    out = grid.fit(nus=(0.5, 1.5, 2.5, float("inf")), penalizations=tuple(np.logspace(-8, 2, 11)))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t
+    return {"grid_s": dt, "points": len(out), "independent_fits_s": None if single_fit_s is None else 44 * single_fit_s,
+            "per_kernel": {str(k): v for k, v in grid.times["kernels"].items()}, "prepare_s": grid.times["prepare"],
+            "workload": f"4 nu x 11 penalizations, matern sigma 10, n={n}, p={p}, M={M}, d={d} (device-resident inputs)"}
+
+
 def leg_baseline_b():
     """BASELINE.md Baseline B: the reference's OWN KRRApprox(method='sklearn') at config 1 (exact KRR, CPU)."""
     import importlib.util
@@ -592,6 +614,7 @@ def main():
     if not args.no_extras and world == 1 and cfg_name == "C3":
         torch.cuda.empty_cache()
         line["c2"] = _guard(leg_c2, dev, args)
+        line["grid"] = _guard(leg_grid, dev, line["c2"].get("fit_s"))
         line["c5"] = _guard(leg_c5, dev)
         line["c1"] = _guard(leg_c1, dev)
         if not args.no_cpu_baseline:

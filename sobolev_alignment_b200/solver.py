@@ -254,20 +254,20 @@ class FalkonSolver:
         the columns of the group ride side by side through the two fused-kernel launches.
         """
         ops, pre, M = self.ops, self.pre, self.M
-        dp = states[0][1].B.shape[1]
+        dc = self._group_cols                                 # real (unpadded) columns per penalty
         wide = len(states) > 1
         for j, (k, st) in enumerate(states):
             st.v.copy_(getattr(st, src))
             pre.invA_invT(st.v, st.z, k)                      # v = A_k^-1 u ; z = T^-1 v
             if wide:
-                self.Zw[:, j * dp: (j + 1) * dp] = st.z
+                self.Zw[:, j * dc: (j + 1) * dc] = st.z[:, :dc]
         if wide:
             self._knm_t_knm(self.Zw, self.Ww)                 # W = K_nM^T K_nM [z_1 | z_2 | ...]
         else:
             self._knm_t_knm(states[0][1].z, states[0][1].w)
         for j, (k, st) in enumerate(states):
             if wide:
-                st.w.copy_(self.Ww[:, j * dp: (j + 1) * dp])
+                st.w[:, :dc] = self.Ww[:, j * dc: (j + 1) * dc]
             ops.axpby(1.0 / self.n_total, st.w, 0.0, st.w)    # w /= n
             pre.invTt_invAt(st.w, getattr(st, dst), st.v, self.penalties[k], k)   # A_k^-T (T^-T w + lambda v)
 
@@ -384,14 +384,15 @@ class FalkonSolver:
             self.n_kmv_ += 1
             self.comm.all_reduce(tz)
             del Yd
-            group = max(1, MAX_COLS // dp)
+            group = max(1, MAX_COLS // (c1 - c0))     # penalties per fused launch: their REAL columns side by side
+            self._group_cols = c1 - c0
             tzt = None
             if nl > 1:                       # T^-T of it is shared by all penalties too
                 tzt = tz
                 pre.invTt(tzt)
             for g0 in range(0, nl, group):
                 ks = list(range(g0, min(nl, g0 + group)))
-                self.t_buf = ops.empty(n, len(ks) * dp)
+                self.t_buf = ops.empty(n, dp if len(ks) == 1 else pad_cols(len(ks) * (c1 - c0)))
                 alphas = self._solve_group(tz, tzt, ks, Mp, dp)
                 for k, alpha in zip(ks, alphas):
                     outs[k][:, c0:c1] = alpha[:M, : c1 - c0]
@@ -406,7 +407,8 @@ class FalkonSolver:
         """FALKON solve for the penalties `ks` (sharing the fused-kernel launches); returns [alpha_k] scratch buffers."""
         ops, pre = self.ops, self.pre
         if len(ks) > 1:
-            self.Zw, self.Ww = ops.zeros(Mp, len(ks) * dp), ops.zeros(Mp, len(ks) * dp)
+            wide = pad_cols(len(ks) * self._group_cols)
+            self.Zw, self.Ww = ops.zeros(Mp, wide), ops.zeros(Mp, wide)
         states = []
         for k in ks:
             # B_k = A_k^-T T^-T K_nM^T (Y / n)
