@@ -65,3 +65,27 @@ class EncoderComparison:
             for x in ("source", "target")
         }
         return self
+
+
+def permutation_principal_angles(X: dict, Y: dict, krr_params: dict, n_permutations: int = 10, seed=None):
+    """
+    `SobolevAlignment.permutation_test_number_similar_pvs` (sobolev_alignment.py:1698-1729), numeric core: for every
+    permutation the GENES (columns) of the source and of the target artificial samples are shuffled independently,
+    both KRRs are refitted on the shuffled samples against the unchanged embeddings, and the principal angles
+    (cosines) of the resulting pair are collected.  X / Y: {"source": ..., "target": ...} artificial samples [n x p]
+    and their latent embeddings [n x d]; krr_params: {"source": kwargs, "target": kwargs} of `KRRApprox`.
+    Returns [n_permutations x d] (the reference's `random_principal_angles`); `number_similar_pvs` is then
+    `np.sum(principal_angles > np.percentile(out[:, 0], quantile))`.
+    """
+    from .krr_approx import KRRApprox
+
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n_permutations):
+        krr = {}
+        for side in ("source", "target"):
+            Xs = torch.as_tensor(X[side])
+            perm = torch.from_numpy(rng.permutation(Xs.shape[1])).to(Xs.device)
+            krr[side] = KRRApprox(**krr_params[side]).fit(Xs[:, perm], torch.as_tensor(Y[side]))
+        out.append(EncoderComparison(krr["source"], krr["target"]).compare().principal_vectors().principal_angles)
+    return np.array(out)

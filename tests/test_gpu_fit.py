@@ -297,6 +297,24 @@ def test_fit_with_stored_kernel_blocks():
     assert relerr(clf.transform(Xv), ref.transform(Xv).double()) < 2e-4
 
 
+def test_permutation_principal_angles_drop_for_shuffled_genes():
+    """permutation_test_number_similar_pvs' core: shuffling genes independently on both sides destroys the alignment."""
+    from sobolev_alignment_b200.alignment import permutation_principal_angles
+
+    n, p, d = 1200, 120, 5
+    Xs, Xt = syn.log_counts_numpy(n, p, seed=61), syn.log_counts_numpy(n, p, seed=62)
+    Y = {"source": torch.from_numpy(syn.targets_numpy(Xs, d, seed=63)), "target": torch.from_numpy(syn.targets_numpy(Xt, d, seed=63))}
+    X = {"source": torch.from_numpy(Xs), "target": torch.from_numpy(Xt)}
+    kw = dict(method="falkon", kernel="laplacian", kernel_params={"sigma": 6.0}, penalization=1e-5, M=250,
+              falkon_options={"center_seed": 1})
+    params = {"source": kw, "target": kw}
+    true = EncoderComparison(KRRApprox(**kw).fit(X["source"], Y["source"]),
+                             KRRApprox(**kw).fit(X["target"], Y["target"])).compare().principal_vectors().principal_angles
+    rand = permutation_principal_angles(X, Y, params, n_permutations=3, seed=0)
+    assert rand.shape == (3, d) and np.all(rand <= 1 + 1e-6) and np.all(rand >= -1e-6)
+    assert np.sum(true > np.percentile(rand[:, 0], 95)) >= 1     # the same encoder on both sides: similar PVs survive
+
+
 # ---------------------------------------------------------------------------- row-sharded fit on the real engine
 def _sharded_rank_main(rank, world, port, out_dir):
     import os
