@@ -59,8 +59,13 @@ constexpr int NCONS = 8;                     // consumer warps
 constexpr int THREADS = (NCONS + 2) * 32;
 constexpr int SYNC_HDR = 64;                 // ints in front of the flags
 enum { KIND_DEP = 0, KIND_INV = 1, KIND_W = 2 };
+constexpr int LL_DEPS = 3;                   // a finishing row takes its last LL_DEPS dependencies (and the W tile's x) through
+                                             // the low-latency buffer: see "publication" below
+constexpr unsigned LL_TAG = 0x5AB00001u;
 
 __host__ __device__ constexpr int xhat_bytes(int nb8) { return 2 * nb8 * 8 * 256 + 16; }
+// 8-byte words {fp16 hi | fp16 lo, tag} of one converted block in the low-latency buffer (+ one word for its scale)
+__host__ __device__ constexpr int ll_words(int nb8) { return TS * nb8 * 8 + 2; }
 
 struct Job {
   const uint8_t* tiles;  // packed strictly-lower tiles
@@ -78,6 +83,7 @@ struct Params {
                     // 1 partial-sum count (by chain row), 2 fp32 x written (by block)
   float* partial;   // [njobs][nblk][128 x 32]
   uint8_t* xhat;    // [njobs][nblk][xhat_bytes]
+  uint2* ll;        // [njobs][nblk][ll_words]: low-latency copy of the converted x (zeroed by the launch)
   long long* trace; // developer tool (option SAB_TRSM_TRACE_PTR): 8 globaltimer stamps per block of job 0
 };
 
@@ -110,6 +116,35 @@ __device__ __forceinline__ void wait_flag_ge(const int* f, int want, int what, u
       else if (now - t0 > 4000000000ull) {
         printf("sobolev_b200: trsm wait timed out (cta %d thread %d waiting for %d >= %d)\n", blockIdx.x,
                threadIdx.x, what, want);
+        __trap();
+      }
+    }
+  }
+}
+
+// Low-latency publication (the idea of NCCL's LL protocol): every 8-byte word carries 4 bytes of payload and a tag,
+// written with one volatile 8-byte store and polled with volatile 8-byte loads -- the data is its own flag, so the chain
+// needs neither a fence on the producer side nor a separate flag round trip + copy on the consumer side.
+__device__ __forceinline__ void ll_store(uint2* p, uint32_t payload) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(LL_TAG) : "memory");
+}
+__device__ __forceinline__ uint2 ll_load(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ll_wait(const uint2* p, uint2 v) {
+  if (v.y == LL_TAG) return v.x;
+  unsigned spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    v = ll_load(p);
+    if (v.y == LL_TAG) return v.x;
+    if ((++spins & 0x3FFu) == 0) {
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {
+        printf("sobolev_b200: trsm low-latency wait timed out (cta %d thread %d)\n", blockIdx.x, threadIdx.x);
         __trap();
       }
     }
@@ -339,8 +374,11 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
         const int kd = kind_of(it, i);
         const int s = xg % NXSLOT;
         mbar_wait(smem_u32(&sm.xempty[s]), ((xg / NXSLOT) & 1) ^ 1);
+        // tiles whose operand the consumers fetch themselves: the inverse product, and -- on a finishing row -- the
+        // freshest dependencies, which come through the low-latency buffer
+        const bool ll = it.fin && (kd == KIND_W || (kd == KIND_DEP && i >= it.ndep - LL_DEPS));
         if (lane == 0) {
-          if (kd == KIND_INV) {
+          if (kd == KIND_INV || ll) {
             mbar_arrive(smem_u32(&sm.xfull[s]));
           } else {
             const int dep = kd == KIND_DEP ? it.k0 + i : it.c - 1;   // chain index of the block whose x is needed
@@ -494,9 +532,30 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
           store_operand(xslot, v, sc);
           fence_proxy_async_smem();   // the slot is refilled by cp.async.bulk later: order these generic writes before it
           consumer_bar();
+        } else if (it.fin && (kd == KIND_W || i >= it.ndep - LL_DEPS)) {
+          // low-latency fetch: every thread polls the 4 NB8 words of ITS fragment positions (same thread -> word map
+          // as the publisher) plus the scale word, and drops the halves into the handed-over slot
+          const int dep = kd == KIND_DEP ? it.k0 + i : it.c - 1;
+          const uint2* src = p.ll + (static_cast<long long>(it.job) * nblk + blk_of(dep)) * ll_words(NB8);
+          const uint2* mine = src + threadIdx.x * (4 * NB8);
+          uint2 w[4 * NB8];
+#pragma unroll
+          for (int e = 0; e < 4 * NB8; ++e) w[e] = ll_load(mine + e);
+          const uint2 ws = ll_load(src + TS * NP);
+#pragma unroll
+          for (int e = 0; e < 4 * NB8; ++e) {
+            const uint32_t pay = ll_wait(mine + e, w[e]);
+            const int nb = e >> 2, q = e & 3;
+            const int n = nb * 8 + 2 * t4 + (q & 1), k = m0 + g8 + (q >> 1) * 8;
+            *reinterpret_cast<uint16_t*>(xslot + xoff(n, k)) = static_cast<uint16_t>(pay & 0xffffu);
+            *reinterpret_cast<uint16_t*>(xslot + NP * 256 + xoff(n, k)) = static_cast<uint16_t>(pay >> 16);
+          }
+          xinv = __uint_as_float(ll_wait(src + TS * NP, ws));
+          if (tr && kd == KIND_W) stamp(blk, 1);
+          fence_proxy_async_smem();
+          consumer_bar();
         } else {
           xinv = *reinterpret_cast<const float*>(xslot + 2 * NP * 256);
-          if (tr && kd == KIND_W) stamp(blk, 1);
         }
         float acc[NB8][4], acx[NB8][4];
 #pragma unroll
@@ -564,6 +623,23 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
         float sc;
         const float inv = pick_scale(block_max(m), sc);   // (its barrier: every warp is done reading the slot)
         if (tr) stamp(blk, 4);
+        {
+          // the chain: 4 NB8 tagged words per thread straight from the registers, no barrier, no fence
+          uint2* dst = p.ll + (static_cast<long long>(it.job) * nblk + blk) * ll_words(NB8);
+          uint2* mine = dst + threadIdx.x * (4 * NB8);
+#pragma unroll
+          for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float sv = U[nb][q] * sc;
+              const __half h = __float2half_rn(sv);
+              const __half l = __float2half_rn(sv - __half2float(h));
+              ll_store(mine + nb * 4 + q, static_cast<uint32_t>(__half_as_ushort(h)) |
+                                              (static_cast<uint32_t>(__half_as_ushort(l)) << 16));
+            }
+          if (threadIdx.x == 0) ll_store(dst + TS * NP, __float_as_uint(inv));
+          if (tr) stamp(blk, 6);
+        }
         const int xs = (T - 1) % NXSLOT;
         uint8_t* stage = xring + xs * XB;
         store_operand(stage, U, sc);
@@ -582,7 +658,6 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
           __threadfence();
           fence_proxy_async_all();
           st_release_gpu(pub + blk, 1);
-          if (tr) stamp(blk, 6);
         }
 #pragma unroll
         for (int nb = 0; nb < NB8; ++nb) {
@@ -987,6 +1062,7 @@ extern "C" int64_t sa_trsm_workspace_bytes(int64_t M) {
   b = (b + 255) / 256 * 256;
   b += 2 * nblk * TS * 32 * 4;                 // partial sums
   b += 2 * nblk * ((xhat_bytes(4) + 127) / 128 * 128);   // converted x blocks
+  b += 2 * nblk * static_cast<int64_t>(ll_words(4)) * 8;     // their low-latency copies
   return b + 256;
 }
 
@@ -1009,6 +1085,9 @@ static int solve_jobs(cudaStream_t st, Params& p, int64_t M, int dp, int transpo
   p.partial = reinterpret_cast<float*>(ws + off);
   off += 2ll * nblk * TS * 32 * 4;
   p.xhat = ws + off;
+  off += 2ll * nblk * ((xhat_bytes(4) + 127) / 128 * 128);
+  p.ll = reinterpret_cast<uint2*>(ws + off);
+  SAB_CHECK_CUDA(cudaMemsetAsync(p.ll, 0, static_cast<size_t>(p.njobs) * nblk * ll_words(4) * 8, st));
   {
     char tp[64];
     p.trace = option("SAB_TRSM_TRACE_PTR", tp) ? reinterpret_cast<long long*>(std::strtoull(tp, nullptr, 0)) : nullptr;

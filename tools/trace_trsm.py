@@ -1,7 +1,8 @@
 """Developer tool: globaltimer stamps of the chain steps of one triangular solve (option SAB_TRSM_TRACE_PTR).
 
-Per block of job 0 (a finishing row): 0 x producer saw the flag of block c-1, 1 consumers have its converted x,
-2 W tile landed, 3 W product done, 4 after the block-max barrier, 5 staged copy issued, 6 published, 7 item start.
+Per block of job 0 (a finishing row): 1 consumers have read the converted x of block c-1 from the low-latency buffer,
+2 W tile landed, 3 W product done, 4 after the block-max barrier, 6 low-latency stores of x_c issued (the chain),
+5 plain (bulk-copy) publication issued, 7 item start.
     python tools/trace_trsm.py [M] [dp] [transpose]
 """
 import os
@@ -41,16 +42,15 @@ pub = t[:, 6]
 step = (pub[1:] - pub[:-1]) * 1e-3
 print(f"M={M} dp={dp} transpose={tr}: {nblk} blocks, total {(pub[-1] - pub[0]) * 1e-6:.3f} ms; chain step us: "
       f"mean {step.mean():.2f} median {step.median():.2f} p90 {step.quantile(0.9):.2f} max {step.max():.2f}")
-names = ["flag seen -> x arrived", "x arrived -> W tile landed", "W landed -> product done", "product -> block max",
-         "block max -> staged copy issued", "copy issued -> published", "published(c-1) -> flag seen(c)",
-         "item start -> flag seen"]
+names = ["LL stores of c-1 issued -> x of c-1 read (LL poll)", "x read -> W tile landed", "W landed -> product done",
+         "product -> block max", "block max -> LL stores issued", "item start -> x read"]
 rows = t[1:]
 prev_pub = pub[:-1]
-segs = [rows[:, 1] - rows[:, 0], rows[:, 2] - rows[:, 1], rows[:, 3] - rows[:, 2], rows[:, 4] - rows[:, 3],
-        rows[:, 5] - rows[:, 4], rows[:, 6] - rows[:, 5], rows[:, 0] - prev_pub, rows[:, 0] - rows[:, 7]]
+segs = [rows[:, 1] - prev_pub, rows[:, 2] - rows[:, 1], rows[:, 3] - rows[:, 2], rows[:, 4] - rows[:, 3],
+        rows[:, 6] - rows[:, 4], rows[:, 1] - rows[:, 7]]
 for nm, sg in zip(names, segs):
     sg = sg * 1e-3
-    print(f"  {nm:34s} mean {sg.mean():7.2f} us  median {sg.median():7.2f}  p90 {sg.quantile(0.9):7.2f}")
+    print(f"  {nm:52s} mean {sg.mean():7.2f} us  median {sg.median():7.2f}  p90 {sg.quantile(0.9):7.2f}")
 for lo in range(0, nblk - 1, max(1, nblk // 8)):
     hi = min(nblk - 1, lo + max(1, nblk // 8))
     print(f"  blocks {lo:4d}-{hi:4d}: {(pub[hi] - pub[lo]) * 1e-3 / (hi - lo):.2f} us per step")
