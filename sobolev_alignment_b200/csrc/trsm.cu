@@ -123,34 +123,18 @@ __device__ __forceinline__ void wait_flag_ge(const int* f, int want, int what, u
 }
 
 // Low-latency publication (the idea of NCCL's LL protocol): every 8-byte word carries 4 bytes of payload and a tag,
-// written with one volatile 8-byte store and polled with volatile 8-byte loads -- the data is its own flag, so the chain
+// written with one relaxed (gpu scope) 8-byte store and polled with relaxed 8-byte loads -- single-copy atomic at that
+// size, free to overlap each other (volatile accesses of a thread serialise: 12 words took 1.6 us to store and 4.4 us to
+// read in the first version of this path) -- so the data is its own flag and the chain
 // needs neither a fence on the producer side nor a separate flag round trip + copy on the consumer side.
 __device__ __forceinline__ void ll_store(uint2* p, uint32_t payload) {
-  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(LL_TAG) : "memory");
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(LL_TAG) : "memory");
 }
 __device__ __forceinline__ uint2 ll_load(const uint2* p) {
   uint2 v;
-  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ uint32_t ll_wait(const uint2* p, uint2 v) {
-  if (v.y == LL_TAG) return v.x;
-  unsigned spins = 0;
-  unsigned long long t0 = 0;
-  for (;;) {
-    v = ll_load(p);
-    if (v.y == LL_TAG) return v.x;
-    if ((++spins & 0x3FFu) == 0) {
-      const unsigned long long now = global_timer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) {
-        printf("sobolev_b200: trsm low-latency wait timed out (cta %d thread %d)\n", blockIdx.x, threadIdx.x);
-        __trap();
-      }
-    }
-  }
-}
-
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -537,20 +521,42 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
           // as the publisher) plus the scale word, and drops the halves into the handed-over slot
           const int dep = kd == KIND_DEP ? it.k0 + i : it.c - 1;
           const uint2* src = p.ll + (static_cast<long long>(it.job) * nblk + blk_of(dep)) * ll_words(NB8);
-          const uint2* mine = src + threadIdx.x * (4 * NB8);
-          uint2 w[4 * NB8];
+          // word (thread, e) sits at e * 256 + thread: a warp's access is 256 contiguous bytes (element-major; the
+          // thread-major layout of the first version cost 32 partial sectors per instruction: 4.3 us per read)
+          const uint2* mine = src + threadIdx.x;
+          // every round re-issues ALL loads of the thread at once (one L2 round trip per round, not one per stale word)
+          uint2 w[4 * NB8], ws;
+          {
+            unsigned spins = 0;
+            unsigned long long t0 = 0;
+            for (;;) {
 #pragma unroll
-          for (int e = 0; e < 4 * NB8; ++e) w[e] = ll_load(mine + e);
-          const uint2 ws = ll_load(src + TS * NP);
+              for (int e = 0; e < 4 * NB8; ++e) w[e] = ll_load(mine + e * (NCONS * 32));
+              ws = ll_load(src + TS * NP);
+              bool ok = ws.y == LL_TAG;
+#pragma unroll
+              for (int e = 0; e < 4 * NB8; ++e) ok = ok && (w[e].y == LL_TAG);
+              if (ok) break;
+              if ((++spins & 0x3FFu) == 0) {
+                const unsigned long long now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 4000000000ull) {
+                  printf("sobolev_b200: trsm low-latency wait timed out (cta %d thread %d block %d)\n", blockIdx.x,
+                         threadIdx.x, blk_of(dep));
+                  __trap();
+                }
+              }
+            }
+          }
 #pragma unroll
           for (int e = 0; e < 4 * NB8; ++e) {
-            const uint32_t pay = ll_wait(mine + e, w[e]);
+            const uint32_t pay = w[e].x;
             const int nb = e >> 2, q = e & 3;
             const int n = nb * 8 + 2 * t4 + (q & 1), k = m0 + g8 + (q >> 1) * 8;
             *reinterpret_cast<uint16_t*>(xslot + xoff(n, k)) = static_cast<uint16_t>(pay & 0xffffu);
             *reinterpret_cast<uint16_t*>(xslot + NP * 256 + xoff(n, k)) = static_cast<uint16_t>(pay >> 16);
           }
-          xinv = __uint_as_float(ll_wait(src + TS * NP, ws));
+          xinv = __uint_as_float(ws.x);
           if (tr && kd == KIND_W) stamp(blk, 1);
           fence_proxy_async_smem();
           consumer_bar();
@@ -626,7 +632,7 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
         {
           // the chain: 4 NB8 tagged words per thread straight from the registers, no barrier, no fence
           uint2* dst = p.ll + (static_cast<long long>(it.job) * nblk + blk) * ll_words(NB8);
-          uint2* mine = dst + threadIdx.x * (4 * NB8);
+          uint2* mine = dst + threadIdx.x;
 #pragma unroll
           for (int nb = 0; nb < NB8; ++nb)
 #pragma unroll
@@ -634,7 +640,7 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
               const float sv = U[nb][q] * sc;
               const __half h = __float2half_rn(sv);
               const __half l = __float2half_rn(sv - __half2float(h));
-              ll_store(mine + nb * 4 + q, static_cast<uint32_t>(__half_as_ushort(h)) |
+              ll_store(mine + (nb * 4 + q) * (NCONS * 32), static_cast<uint32_t>(__half_as_ushort(h)) |
                                               (static_cast<uint32_t>(__half_as_ushort(l)) << 16));
             }
           if (threadIdx.x == 0) ll_store(dst + TS * NP, __float_as_uint(inv));
