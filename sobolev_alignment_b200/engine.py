@@ -143,7 +143,12 @@ class CudaOps:
     def alloc_prepared(self, n: int, p: int) -> nat.Prepared:
         return nat.alloc_prepared(n, p, self.device)
 
-    def prepare(self, X: torch.Tensor, frame: Frame, out: nat.Prepared | None = None) -> nat.Prepared:
+    def stage_buffers(self, n: int, p: int):
+        """Device fp32 chunk buffers of the pinned-input staging path (allocate them on the stream that will free them)."""
+        rows = max(1, min(self.stage_rows, n))
+        return [torch.empty(rows, p, dtype=torch.float32, device=self.device) for _ in range(min(2, -(-n // rows)))]
+
+    def prepare(self, X: torch.Tensor, frame: Frame, out: nat.Prepared | None = None, dev_bufs=None) -> nat.Prepared:
         """
         Rows of X (CPU or CUDA, any float dtype) -> prepared fp16 operand resident on the device (`out`, when
         given, must hold exactly X.shape[0] rows: the streaming callers reuse two buffers).
@@ -165,7 +170,8 @@ class CudaOps:
         if self.stages_without_host_work(X):
             # pinned fp32 rows: H2D straight from the caller's buffer; everything is ordered by the stream (two
             # device chunk buffers reused in stream order), the host only enqueues
-            dev_bufs = [torch.empty(rows, p, dtype=torch.float32, device=self.device) for _ in range(min(2, -(-n // rows)))]
+            if dev_bufs is None:
+                dev_bufs = self.stage_buffers(n, p)
             for i, s in enumerate(range(0, n, rows)):
                 e = min(n, s + rows)
                 buf = dev_bufs[i & 1][: e - s]

@@ -47,6 +47,24 @@ class _HostFetch:
         return self._out
 
 
+def _gather_rows(X: torch.Tensor, idx: np.ndarray) -> torch.Tensor:
+    """X[idx] -- for host tensors split over a few threads (torchrun pins OMP to one thread; index_select drops the GIL)."""
+    index = torch.from_numpy(np.ascontiguousarray(idx)).to(X.device)
+    if X.is_cuda or len(idx) * X.shape[1] < (1 << 22):
+        return X[index]
+    from concurrent.futures import ThreadPoolExecutor
+
+    T = 8
+    out = torch.empty(len(idx), X.shape[1], dtype=X.dtype)
+    step = (len(idx) + T - 1) // T
+    with ThreadPoolExecutor(max_workers=T) as pool:
+        futs = [pool.submit(torch.index_select, X, 0, index[a: a + step], out=out[a: a + step])
+                for a in range(0, len(idx), step)]
+        for f in futs:
+            f.result()
+    return out
+
+
 class Falkon:
     def __init__(self, kernel, penalty: float, M: int, center_selection="uniform", maxiter: int = 20,
                  seed=None, error_fn=None, error_every=1, weight_fn=None, options: FalkonOptions | None = None):
@@ -110,7 +128,7 @@ class Falkon:
         else:
             t_gather = 0.0
             idx = self._select_centres(n_local)
-            centres = X.rows(idx) if deferred else X[torch.from_numpy(idx).to(X.device)]
+            centres = X.rows(idx) if deferred else _gather_rows(X, idx)
             n_total = n_local
             t_gather = time.perf_counter() - t0
         # Row-sharded fit from host inputs: `ny_points_` has to be a host tensor again (anchors() contract).
@@ -161,7 +179,7 @@ class Falkon:
                              "all ranks draw the same centres")
         idx = self._select_centres(n_total)
         mine = idx[(idx >= offsets[comm.rank]) & (idx < offsets[comm.rank + 1])] - offsets[comm.rank]
-        rows = X.rows(mine) if hasattr(X, "folded") else ops.to_device(X[torch.from_numpy(mine).to(X.device)])
+        rows = X.rows(mine) if hasattr(X, "folded") else ops.to_device(_gather_rows(X, mine))
         p = X.shape[1]
         full = ops.zeros(len(idx), p)
         pos = np.nonzero((idx >= offsets[comm.rank]) & (idx < offsets[comm.rank + 1]))[0]
