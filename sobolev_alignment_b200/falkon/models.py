@@ -17,8 +17,16 @@ from ..solver import Comm, FalkonSolver, Predictor
 from .options import FalkonOptions
 
 
+_pinned_fetch = {}      # (device index) -> pinned staging buffer of the centre read-back, reused across fits
+
+
 class _HostFetch:
-    """Device -> host copy of a tensor on its own stream and thread, overlapped with whatever the caller enqueues."""
+    """
+    Device -> host copy of a tensor on its own stream and thread, overlapped with whatever the caller enqueues.
+    The D2H itself goes through a cached PINNED buffer (a pageable cudaMemcpy is staged by the driver in blocking
+    chunks and, from a second thread, stalls the main thread's kernel launches: 0.3 s per fit at 8 GPUs); the
+    pinned -> pageable copy that follows is plain host work.
+    """
 
     def __init__(self, t: torch.Tensor):
         import threading
@@ -32,8 +40,18 @@ class _HostFetch:
         def run():
             try:
                 torch.cuda.set_device(t.device)
+                key = t.device.index
+                buf = _pinned_fetch.get(key)
+                if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
+                    buf = torch.empty(t.numel(), dtype=t.dtype).pin_memory()
+                    _pinned_fetch[key] = buf
+                view = buf[: t.numel()].view(t.shape)
                 with torch.cuda.stream(side):
-                    self._out = t.to("cpu")
+                    view.copy_(t, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                done.synchronize()
+                self._out = view.clone()          # pageable result the caller owns; the pinned buffer is reused
             except BaseException as exc:  # noqa: BLE001 - re-raised by result()
                 self._err = exc
 
