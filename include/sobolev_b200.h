@@ -42,7 +42,7 @@ enum {
 int sa_version(void);
 const char* sa_last_error(void);
 
-/* Tuning / diagnostic options, e.g. sa_set_option("SAB_TRSM_CHUNK", "32").  The
+/* Tuning / diagnostic options, e.g. sa_set_option("SAB_TRSM_CHUNK", "64").  The
  * SAB_* environment variable of the same name is the default, read once at its first use; value NULL
  * restores it.  Not on the reference's path. */
 int sa_set_option(const char* name, const char* value);

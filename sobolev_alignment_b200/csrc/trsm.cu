@@ -18,7 +18,7 @@
 //     one -- costs ONE tile product on the chain:
 //       x_c = inv(L_cc) (b_c - sum_{k < c-1} L(c, k) x_k) - Wf[c] x_{c-1}.
 //
-// The solve is one persistent launch (one CTA per SM).  Work items = (job, block row, chunk of <= CH
+// The solve is one persistent launch (one CTA per SM).  Work items = (job, block row, chunk of <= CH = 512
 // dependency tiles); a CTA draws items from an atomic ticket in an order in which every item only waits
 // for items with smaller tickets (chunk column by chunk column, rows top-down, the jobs of a pair
 // interleaved), so heavy block rows are spread over many CTAs and the chain never waits for a CTA that
@@ -982,10 +982,13 @@ premul_kernel(const float* __restrict__ L, long long ldl, const float* __restric
   }
 }
 
-// dependency tiles per work item (tuning knob SAB_TRSM_CHUNK)
+// dependency tiles per work item (tuning knob SAB_TRSM_CHUNK).  Measured on B200 (tools/gpu_sweep.sh, pair at
+// M = 50 048 / 100 096): 16 -> 2.65 / 8.4 ms, 64 -> 2.4 / 7.5, 256 -> 2.1 / 6.9, 512 -> 2.1 / 6.7, 1024 -> 2.1 / 7.0:
+// every chunk-column boundary stalls the chain for one bulk item, so long chunks win until the rows of the very
+// largest factors stop balancing.
 static int chunk_tiles() {
-  const int c = option_int("SAB_TRSM_CHUNK", 16);
-  return c < 2 ? 2 : (c > 256 ? 256 : c);
+  const int c = option_int("SAB_TRSM_CHUNK", 512);
+  return c < 2 ? 2 : (c > 4096 ? 4096 : c);
 }
 static int sm_count() {
   static const int v = [] {

@@ -460,12 +460,12 @@ def test_cholesky_ltl_trsm(cuda_ops, M, dp, nb, sab_option):
 
 
 @pytest.mark.parametrize("M,dp,chunk", [(128, 4, None), (1024, 20, None), (4096, 12, None), (4096, 28, "4"),
-                                        (2304, 8, "2")])
+                                        (2304, 8, "2"), (4096, 20, "16")])
 def test_paired_solves_match_two_single_solves(cuda_ops, M, dp, chunk, sab_option):
     """
     sa_trsm_solve_pair (two interleaved chains in one launch) against two sa_trsm_solve calls and against
     float64, both directions, with the lambda V term; several chunk lengths of the work decomposition
-    (option SAB_TRSM_CHUNK; the default is 16 tiles per item).
+    (option SAB_TRSM_CHUNK; the default is 512 tiles per item -- a single chunk column up to M = 65 536).
     """
     from sobolev_alignment_b200 import _native as nat
 

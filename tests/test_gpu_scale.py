@@ -84,7 +84,7 @@ def test_fit_parity_baseline_config2():
 
 
 def test_fit_parity_matern_many_block_solves():
-    """Matern nu = 1.5 (the config-4 kernel) with M = 24 576: 192-block factors, 1 200+ work items per solve."""
+    """Matern nu = 1.5 (the config-4 kernel) with M = 24 576: 192-block factors (more block rows than SMs)."""
     n, p, M, d, nv = 60_000, 384, 24_576, 6, 512
     dev = torch.device("cuda")
     Xall = syn.log_counts_torch(n + nv, p, seed=6, device=dev)
