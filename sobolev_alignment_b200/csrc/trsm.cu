@@ -444,11 +444,13 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
       const long long frow = static_cast<long long>(blk) * TS + m0 + g8;   // global row of fragment rows (+8)
       if (tr) stamp(blk, 7);
 
-      float S[NB8][4], U[NB8][4];
+      // S: running sum over the eliminated dependencies; Sb: the current group of 16 -- two-level summation, so the
+      // rounding error grows with 16 + (tiles / 16) additions instead of with the (up to 512) tiles of an item
+      float S[NB8][4], Sb[NB8][4], U[NB8][4];
 #pragma unroll
       for (int nb = 0; nb < NB8; ++nb)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) S[nb][q] = U[nb][q] = 0.f;
+        for (int q = 0; q < 4; ++q) S[nb][q] = Sb[nb][q] = U[nb][q] = 0.f;
 
       // S += the partial sum the previous item of this block row left behind (fixed order: item q-1 before q)
       auto add_previous_partial = [&]() {
@@ -597,10 +599,19 @@ __global__ void __launch_bounds__(THREADS, 1) trsm_solve_kernel(const Params p) 
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float pv = (acc[nb][q] + acx[nb][q]) * r;
-            if (kd == KIND_DEP) S[nb][q] += pv;
+            if (kd == KIND_DEP) Sb[nb][q] += pv;
             else if (kd == KIND_INV) U[nb][q] = pv;
             else U[nb][q] -= pv;
           }
+        if (kd == KIND_DEP && (((it.k0 + i) & 15) == 15 || i + 1 == it.ndep)) {
+#pragma unroll
+          for (int nb = 0; nb < NB8; ++nb)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              S[nb][q] += Sb[nb][q];
+              Sb[nb][q] = 0.f;
+            }
+        }
       }
 
       if (!it.fin) {
