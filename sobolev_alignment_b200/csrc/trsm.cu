@@ -31,8 +31,19 @@
 //   warps 0-7 (consumers)      16 output rows each: ldmatrix + mma.sync.m16n8k16 (hi hi + lo hi + hi lo),
 //                              fp32 accumulators in registers; the publisher of a block converts its x
 //                              ONCE for all later consumers.
-// Partial sums of a block row travel between its items through global memory in item order (fixed
-// summation order: the result is bit-reproducible, which the row-sharded solver relies on).
+// Partial sums of a block row travel between its items through global memory in item order, and inside an
+// item the dependency products are summed in groups of 16 (two-level summation: the rounding error does not
+// grow with the length of a row): fixed summation order, so the result is bit-reproducible, which the
+// row-sharded solver relies on.
+//
+// The chain itself -- block c needs x_{c-1} -- runs through a low-latency buffer: the publisher's threads write
+// their fragment as 8-byte {payload, tag} words (relaxed, gpu scope) and the next rows poll exactly those words,
+// so a chain step carries no fence, no flag round trip and no copy (see ll_store / ll_load below; measured anatomy
+// of a step in profiles/r02_trsm_chain_trace.txt).  Older dependencies and all non-finishing items use the flag +
+// bulk-copy route of warp 9.
+//
+// The same tile image and tile product serve `sa_ktv` (K^T t from a stored kernel block, the optional design (B) of
+// the CG product pair): see the section in front of the packing kernels.
 //
 // sa_trsm_solve_pair runs the two dependent solves the FALKON operator always applies back to back
 // (A^-1 then T^-1; T^-T, + lambda v, then A^-T) as two interleaved chains of one launch: job 1's block c
