@@ -301,7 +301,7 @@ def _potrf_rank_main(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 def test_distributed_potrf_gloo(tmp_path, world):
     """Outer panels dealt out over the ranks, panels broadcast with one step of look-ahead: every rank ends with the full factor."""
     port = _free_port()
