@@ -1,4 +1,4 @@
-"""Sustained-throughput sweep of the fused kernel over its launch-time knobs (env, read per launch).
+"""Sustained-throughput sweep of the fused kernel over its launch-time knobs (library options).
 
 python tools/sweep_kmv.py [seconds_per_config]
 Each configuration runs back to back for ~seconds_per_config so the power-capped clock settles; the SM
@@ -31,8 +31,9 @@ def smi():
 
 def run(mode, env):
     for k in ("SAB_STAGES", "SAB_CTA_GROUP", "SAB_DEBUG", "SAB_NSPLIT", "SAB_L2_BUDGET_MB", "SAB_VBUFS"):
-        os.environ.pop(k, None)
-    os.environ.update({k: str(v) for k, v in env.items()})
+        nat.set_option(k, None)
+    for k, v in env.items():
+        nat.set_option(k, v)        # (environment variables are read once per process: set the options explicitly)
     a, b = (rows, 50000) if mode == "fwd" else (50000, rows)
     g = torch.Generator(device=dev).manual_seed(0)
     A = torch.randn(a, p, device=dev, generator=g) * 0.2
